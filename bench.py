@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py - PCG iterations/s and SpMV GB/s (fp64) on B200, next to the CPU reference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--block 128]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1] at N=1, the C5 stacking rule at N>1, weak scaling): every GPU owns
+one box of `block`^3 trilinear hex elements (default 128^3: n = 6 390 144 free dofs, nnz = 509 597 550,
+6.1 GB of CSR per GPU - far larger than the 126 MB L2) of a global mesh stacked 1x1x1 / 2x1x1 / 2x2x1 /
+2x2x2, clamped at x = 0, traction on x = max; the matrix is generated on the device.  A "step" is one
+PCG iteration (CSR SpMV + 2 reductions + Jacobi + AXPYs [+ halo exchange + allreduces]).
+
+    value    K iterations / device time of the iteration loop (CUDA events on the solver stream, max over ranks)
+    e2e      the same K iterations through the public solve() with HOST buffers: b from pinned host memory,
+             x back to the host, setup / verification matvecs and all host polling inside the timed region
+    roofline the merge-path SpMV kernel: algorithmic bytes (12 nnz + 4|8 (n+1) + 16 n) / mean launch duration
+             (event pairs around every SpMV launch of a separate K-iteration pass) against MEASURED_PEAKS.json
+    cpu_baseline / --impl reference: the oracle port of the reference's numpy element-by-element PCG
+             (oracle/ref_pcg.py <- pcg_solver.py:242-598) on the same mesh, one process per part like
+             `mpiexec -np P`, bounded to a few iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+
+# the reference pins every BLAS to one thread per rank BEFORE numpy is imported (pcg_solver.py:10-15);
+# the CPU arm forks one process per mesh part, so the same must hold here
+for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "PCG iterations/sec (fp64 Jacobi-PCG, CSR SpMV) on 3-D elastostatic hex mesh"
+UNIT = "iterations/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------- CPU reference arm
+def _cpu_rank(rank, nparts, ng, pgrid, iters, conn):
+    """One 'MPI rank' of the oracle port: its own box, lock-step PCG via pipes is overkill for a timing
+    sample, so every rank runs the per-rank work of an iteration (EBE matvec + the vector ops) on its own
+    box and the wall time of the slowest rank is taken, like a barrier-synchronised iteration."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        os.sched_setaffinity(0, {rank % os.cpu_count()})
+    except Exception:
+        pass
+    from oracle import ref_pcg as R
+    from oracle.hex_parts import hex_box_part
+    from pcg_mpi_solver_b200.hexmesh import partition_blocks
+    blk = partition_blocks(ng, pgrid)[rank]
+    part = R.EbePart(hex_box_part(blk.ng, blk.e0, blk.ne, rank, h=1.0 / ng[0]))
+    R.update_bc([part])
+    op = R.Operator([part])
+    minv = op.jacobi()
+    conn.send("ready")
+    conn.recv()
+    nglob = 3 * (ng[0]) * (ng[1] + 1) * (ng[2] + 1)
+    t0 = time.perf_counter()
+    R.ref_pcg([part], minv, 1e-300, 1, nglob=nglob)
+    t1 = time.perf_counter()
+    out = R.ref_pcg([part], minv, 1e-300, 1 + iters, nglob=nglob)
+    t2 = time.perf_counter()
+    # difference of two runs = `iters` loop iterations only (set-up and the two residual matvecs cancel)
+    conn.send(((t2 - t1) - (t1 - t0), out["Iter"], part.n))
+
+
+def cpu_reference(ng, iters, max_procs=None):
+    """iterations/s of the oracle port on this host: the mesh is cut into P slabs/boxes (P = cores, power
+    of two, <= 64), one process per part and one BLAS thread per process exactly like the reference's
+    `mpiexec -np P` with OMP_NUM_THREADS=1 (pcg_solver.py:10-15); interface exchange is omitted (it is
+    < 10 % of the reference's time, solver_demo.ipynb:380-408) which favours the CPU side."""
+    import multiprocessing as mp
+    from pcg_mpi_solver_b200.hexmesh import block_grid
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    p = 1
+    while p * 2 <= min(cores, max_procs or 64):
+        p *= 2
+    pgrid = block_grid(p)
+    ctx = mp.get_context("fork")
+    procs, conns = [], []
+    for r in range(p):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_cpu_rank, args=(r, p, ng, pgrid, iters, b))
+        pr.start()
+        procs.append(pr)
+        conns.append(a)
+    for c in conns:
+        c.recv()
+    for c in conns:
+        c.send("go")
+    res = [c.recv() for c in conns]
+    for pr in procs:
+        pr.join()
+    dt = max(r[0] for r in res)
+    return {"value": iters / dt, "unit": UNIT, "cores": p, "kind": "port",
+            "sample": f"{iters} PCG loop iterations (difference of a {iters}+1 and a 1 iteration run) of the numpy element-by-element reference path on the same "
+                      f"{ng[0]}x{ng[1]}x{ng[2]} hex mesh cut into {p} boxes, 1 process/box, 1 BLAS thread each, no interface exchange",
+            "seconds": dt}
+
+
+# --------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--block", type=int, default=int(os.environ.get("PCGB_BENCH_BLOCK", "128")), help="hex elements per axis per GPU")
+    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+
+    from pcg_mpi_solver_b200.hexmesh import block_grid
+    pgrid = block_grid(max(world, 1))
+    ng = tuple(args.block * pgrid[a] for a in range(3))
+    config = {"workload": f"hex{args.block}^3 elements per GPU, global {ng[0]}x{ng[1]}x{ng[2]} trilinear hex elastostatics "
+                          f"(E=1, nu=0.3, h=1/{ng[0]}), clamped x=0, traction on x=max, Jacobi-PCG fixed {K} iterations",
+              "per_gpu_block": args.block, "process_grid": list(pgrid), "parallelism": f"dd{world}",
+              "l2_policy": "inputs larger than L2 (CSR 6.1 GB per GPU vs 126 MB L2), no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        iters = max(1, min(args.steps, args.cpu_iters))
+        for _ in range(0):
+            pass
+        base = cpu_reference(ng if world == 1 else tuple(args.block * g for g in pgrid), iters)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+                "warmup": 0, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pcg_mpi_solver_b200 import solve
+    from pcg_mpi_solver_b200.hexmesh import generate_matrix, interface_lists, load_vector, partition_blocks
+    from pcg_mpi_solver_b200.solver import Communicator, SubdomainOperator
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = Communicator.from_torch_distributed(dev)
+
+    blocks = partition_blocks(ng, pgrid)
+    blk = blocks[rank]
+    blk.h = 1.0 / ng[0]
+    for b_ in blocks:
+        b_.h = blk.h
+    A = generate_matrix(blk, device=dev)
+    nbr, lists, w = interface_lists(blocks, rank) if world > 1 else ([], [], None)
+    n_global = 3 * ng[0] * (ng[1] + 1) * (ng[2] + 1)
+    op = SubdomainOperator(A, comm, nbr, lists, w, n_global=n_global)
+    b = load_vector(blk, device=dev)
+    minv = op.jacobi()
+    n = A.shape[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also builds the CUDA graph of the iteration batch)
+    op.solve(b, minv, 0.0, W, fixed_iters=True, check_every=min(W, 50))
+    op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50)
+    barrier()
+
+    # ---- timed region: exactly K iterations, device-timed loop
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    x, info = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50)
+    barrier()
+    loop_ms = max_over_ranks(info.loop_ms)
+    assert info.loop_iters == K, (info.loop_iters, K)
+
+    # ---- e2e: public API, host buffers (pinned b in, x out), everything inside the timed region
+    b_host = b.cpu().pin_memory().numpy() if False else b.cpu().numpy()
+    b_pin = torch.from_numpy(b_host).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    b_dev = b_pin.to(dev, non_blocking=True)
+    x_e2e, info_e = op.solve(b_dev, minv, 0.0, K, fixed_iters=True, check_every=50)
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    x_host.copy_(x_e2e, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+
+    # ---- roofline pass: same K iterations with an event pair around every SpMV launch
+    _, info_k = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50, time_kernels=True)
+    spmv_ms = info_k.spmv_ms / max(info_k.spmv_timed, 1)
+    spmv_ms = max_over_ranks(spmv_ms)
+    spmv_share = info_k.spmv_ms / info_k.loop_ms if info_k.loop_ms > 0 else None
+    peak, peak_src = measured_peaks()
+    bytes_spmv = A.spmv_bytes()
+    achieved = bytes_spmv / (spmv_ms * 1e-3) / 1e9
+    iter_bytes = bytes_spmv + 96 * n
+    barrier()
+
+    if rank == 0:
+        value = K / (loop_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": loop_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(config, n_per_gpu=n, nnz_per_gpu=A.nnz, n_global=n_global, plan=A.plan_info(),
+                               halo_bytes_per_exchange=op.halo_bytes()),
+                "dof_iterations_per_s": value * n_global,
+                "e2e": {"value": K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n / K, "d2h_bytes_per_step": 8 * n / K,
+                        "note": "one solve() of K iterations: pinned-host b -> device, K iterations + 2 residual matvecs + host polling, x -> pinned host"},
+                "gpu_launches": int(info.launches),
+                "clocks": clocks,
+                "roofline": {"kernel": "k_spmv_merge (merge-path CSR SpMV, fp64)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_spmv, "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
+                             "spmv_share_of_step": spmv_share,
+                             "iteration": {"algorithmic_bytes": iter_bytes, "achieved_GBps": iter_bytes / (loop_ms / K * 1e-3) / 1e9,
+                                           "frac": iter_bytes / (loop_ms / K * 1e-3) / 1e9 / peak}},
+                "solve_check": {"flag": info.flag, "relres_after_K": info.relres}}
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_reference(ng, max(1, args.cpu_iters))
+            except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

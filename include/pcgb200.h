@@ -113,6 +113,7 @@ typedef struct pcgb_options {
   int32_t use_graph;    /* capture the batch of iterations in a CUDA graph (1) or launch directly (0) */
   int32_t fixed_iters;  /* benchmark mode: ignore convergence, run exactly maxiter iterations */
   int32_t record_resvec; /* keep ||r|| per iteration (reference has this commented out, :428-434) */
+  int32_t time_kernels; /* bracket every SpMV launch of the loop with CUDA events (forces direct launches) */
 } pcgb_options;
 
 typedef struct pcgb_result {
@@ -126,6 +127,10 @@ typedef struct pcgb_result {
   int32_t too_small_tol; /* 1 if the reference would have raised Warning('PCG : TooSmallTolerance') (:549) */
   int64_t matvecs;    /* operator applications performed                                         */
   int64_t launches;   /* CUDA kernel launches issued by this solve (bench 'gpu_launches')        */
+  double loop_ms;     /* device time of the iteration loop only (CUDA events on the solver stream)  */
+  double spmv_ms;     /* sum of the SpMV launch durations inside the loop (time_kernels only)        */
+  int64_t spmv_timed; /* number of SpMV launches in spmv_ms                                         */
+  int64_t loop_iters; /* iterations executed inside the timed loop                                  */
 } pcgb_result;
 
 int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,

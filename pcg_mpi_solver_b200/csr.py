@@ -1,0 +1,90 @@
+"""Device-resident CSR operator: the assembled stiffness matrix A = K[Eff,Eff] of one subdomain.
+
+Reference: the operator of the hot path is calcMatVecProd(..., 'Strain') (pcg_solver.py:242-300),
+an element-by-element product that is never assembled; BASELINE.json's north star prescribes the
+assembled CSR form, so the subdomain builder (partition.py) assembles exactly
+K = sum_e P_e^T (Ck_e S_e Ke S_e) P_e and this class hands it to the merge-path SpMV kernel.
+
+PyTorch tensors are used only as device-memory holders (data_ptr()).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class CsrMatrix:
+    """fp64 values, int32 column indices, int32 or int64 row offsets, all on one CUDA device."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, shape):
+        if not (rowptr.is_cuda and col.is_cuda and val.is_cuda):
+            raise _lib.PcgbError("CsrMatrix needs CUDA tensors (libpcgb200 has no CPU path)")
+        if rowptr.dtype not in (torch.int32, torch.int64) or col.dtype != torch.int32 or val.dtype != torch.float64:
+            raise TypeError("CsrMatrix: rowptr int32/int64, col int32, val float64")
+        self.rowptr, self.col, self.val = rowptr.contiguous(), col.contiguous(), val.contiguous()
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(val.numel())
+        self.device = val.device
+        self._h = ctypes.c_void_p()
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pcgb_csr_create(self.shape[0], self.shape[1], self.nnz, _lib.ptr(self.rowptr),
+                                           1 if rowptr.dtype == torch.int64 else 0, _lib.ptr(self.col),
+                                           _lib.ptr(self.val), _lib.stream_ptr(), ctypes.byref(self._h)),
+                       "pcgb_csr_create")
+
+    # ---- construction helpers --------------------------------------------------------------
+    @classmethod
+    def from_scipy(cls, A, device="cuda", index64=None):
+        A = A.tocsr()
+        A.sort_indices()
+        use64 = bool(index64) if index64 is not None else A.nnz >= 2**31
+        rp = torch.from_numpy(A.indptr.astype(np.int64 if use64 else np.int32)).to(device)
+        col = torch.from_numpy(A.indices.astype(np.int32)).to(device)
+        val = torch.from_numpy(np.ascontiguousarray(A.data, dtype=np.float64)).to(device)
+        return cls(rp, col, val, A.shape)
+
+    # ---- operations ------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._h
+
+    def spmv(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """y = A x through the merge-path kernel."""
+        assert x.is_cuda and x.dtype == torch.float64 and x.numel() == self.shape[1]
+        y = out if out is not None else torch.empty(self.shape[0], dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcgb_spmv(self._h, _lib.ptr(x), _lib.ptr(y), _lib.stream_ptr()), "pcgb_spmv")
+        return y
+
+    def diagonal(self) -> torch.Tensor:
+        d = torch.empty(self.shape[0], dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcgb_csr_diag(self._h, _lib.ptr(d), _lib.stream_ptr()), "pcgb_csr_diag")
+        return d
+
+    def spmv_bytes(self) -> int:
+        """Algorithmic bytes of one SpMV: 12 nnz + R (n+1) + 8 ncols + 8 nrows."""
+        return int(_lib.load().pcgb_spmv_bytes(self._h))
+
+    def plan_info(self) -> dict:
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(_lib.load().pcgb_csr_plan_info(self._h, info))
+        keys = ["ntiles", "tile_items", "lanes", "snap", "split_rows", "smem_bytes", "max_row", "tma"]
+        return dict(zip(keys, [int(v) for v in info]))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()), shape=self.shape)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().pcgb_csr_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass

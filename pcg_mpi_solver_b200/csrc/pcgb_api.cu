@@ -38,6 +38,9 @@ struct pcgb_solver_s {
   PcgCtrl *d_ctrl = nullptr;
   PcgCtrl *h_ctrl = nullptr;    // pinned
   double *h_red = nullptr;      // pinned [8]
+  cudaStream_t own = nullptr;   // the solve runs here: the caller's stream may be the legacy stream, which cannot be captured
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
+  std::vector<cudaEvent_t> ev_k;  // SpMV brackets (time_kernels)
   cudaGraphExec_t gexec = nullptr;
   GraphKey gkey{nullptr, nullptr, nullptr, nullptr, 0};
   int launches = 0;             // launches issued outside graphs (running counter per solve)
@@ -287,6 +290,11 @@ int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_so
   PCGB_CUDA(cudaMalloc(&s->d_ctrl, sizeof(PcgCtrl)));
   PCGB_CUDA(cudaMallocHost(&s->h_ctrl, sizeof(PcgCtrl)));
   PCGB_CUDA(cudaMallocHost(&s->h_red, 8 * sizeof(double)));
+  PCGB_CUDA(cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking));
+  PCGB_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
+  PCGB_CUDA(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
+  PCGB_CUDA(cudaEventCreate(&s->ev_l0));
+  PCGB_CUDA(cudaEventCreate(&s->ev_l1));
   *out = s;
   return PCGB_OK;
 }
@@ -294,6 +302,12 @@ int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_so
 int pcgb_solver_destroy(pcgb_solver_t s) {
   if (!s) return PCGB_OK;
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  if (s->own) cudaStreamDestroy(s->own);
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
+  if (s->ev_l0) cudaEventDestroy(s->ev_l0);
+  if (s->ev_l1) cudaEventDestroy(s->ev_l1);
+  for (cudaEvent_t e : s->ev_k) cudaEventDestroy(e);
   cudaFree(s->r); cudaFree(s->p); cudaFree(s->q); cudaFree(s->xalt); cudaFree(s->partials); cudaFree(s->stage);
   cudaFree(s->red); cudaFree(s->d_ctrl);
   cudaFreeHost(s->h_ctrl); cudaFreeHost(s->h_red);
@@ -348,7 +362,8 @@ int rz_to_device(pcgb_solver_t s, const double *minv, const double *w, cudaStrea
 }
 
 // one PCG iteration enqueued on st (pcg_solver.py:438-562); every kernel no-ops once the state is frozen
-int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, double *xb0, double *resvec, cudaStream_t st, int *nl) {
+int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, double *xb0, double *resvec, cudaStream_t st, int *nl,
+                      cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr) {
   const CsrPlan &P = s->A->P;
   const int64_t n = s->n;
   const int vg = vec_grid(n);
@@ -356,7 +371,9 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   k_pupdate<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, minv, s->p);
   PCGB_CHECK_LAUNCH();
   *nl += 1;
+  if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
   PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
+  if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
   if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
   // p.q : per-tile partials -> (stage) -> scalar.  In the multi-GPU case the partials are those of the
   // UNASSEMBLED local product, whose rank sum equals the reference's weighted dot of the assembled q
@@ -415,11 +432,27 @@ int pcgb_apply(pcgb_solver_t s, const double *d_x, double *d_y, void *stream) {
   return op_apply(s, d_x, d_y, (cudaStream_t)stream);
 }
 
+static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, const double *d_w, double *d_x,
+                    const pcgb_options *opt, double *d_resvec, pcgb_result *res, cudaStream_t st);
+
 int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const double *d_w, double *d_x,
                const pcgb_options *opt, double *d_resvec, pcgb_result *res, void *stream) {
   if (!s || !d_b || !d_x || !opt || !res) return fail(PCGB_ERR_ARG, "pcgb_solve: null argument");
   if (opt->maxiter <= 0) return fail(PCGB_ERR_ARG, "pcgb_solve: maxiter must be positive");
-  cudaStream_t st = (cudaStream_t)stream;
+  // order the solver's own stream after the caller's stream, run, and order the caller's stream after us
+  cudaStream_t user = (cudaStream_t)stream;
+  PCGB_CUDA(cudaEventRecord(s->ev_in, user));
+  PCGB_CUDA(cudaStreamWaitEvent(s->own, s->ev_in, 0));
+  const int rc = solve_on(s, d_b, d_minv, d_w, d_x, opt, d_resvec, res, s->own);
+  if (rc == PCGB_OK) {
+    PCGB_CUDA(cudaEventRecord(s->ev_out, s->own));
+    PCGB_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
+  }
+  return rc;
+}
+
+static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, const double *d_w, double *d_x,
+                    const pcgb_options *opt, double *d_resvec, pcgb_result *res, cudaStream_t st) {
   const int64_t n = s->n;
   const int vg = vec_grid(n);
   memset(res, 0, sizeof(*res));
@@ -478,7 +511,9 @@ int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const d
   int batch = opt->check_every > 0 ? opt->check_every : 16;
   if (batch > opt->maxiter) batch = opt->maxiter;
   const bool multi = s->comm && s->comm->nranks > 1;
-  const bool want_graph = opt->use_graph != 0;
+  const bool want_graph = opt->use_graph != 0 && !opt->time_kernels;
+  size_t kpairs = 0;
+  PCGB_CUDA(cudaEventRecord(s->ev_l0, st));
   int per_iter = 0;
   int flag = 1;
   int too_small = 0;
@@ -507,7 +542,12 @@ int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const d
     } else {
       for (int k = 0; k < batch; ++k) {
         int nl = 0;
-        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, d_x, d_resvec, st, &nl));
+        cudaEvent_t ka = nullptr, kb = nullptr;
+        if (opt->time_kernels && kpairs < 1024) {
+          while (s->ev_k.size() < 2 * (kpairs + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
+          ka = s->ev_k[2 * kpairs]; kb = s->ev_k[2 * kpairs + 1]; ++kpairs;
+        }
+        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, d_x, d_resvec, st, &nl, ka, kb));
         s->launches += nl;
         per_iter = nl;
       }
@@ -545,6 +585,17 @@ int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const d
     break;
   }
   (void)multi;
+  PCGB_CUDA(cudaEventRecord(s->ev_l1, st));
+  PCGB_CUDA(cudaEventSynchronize(s->ev_l1));
+  {
+    float ms = 0.f;
+    PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_l0, s->ev_l1));
+    res->loop_ms = ms;
+    res->loop_iters = c.iter + 1;
+    double tot = 0.0;
+    for (size_t k = 0; k < kpairs; ++k) { float t = 0.f; PCGB_CUDA(cudaEventElapsedTime(&t, s->ev_k[2 * k], s->ev_k[2 * k + 1])); tot += t; }
+    res->spmv_ms = tot; res->spmv_timed = (int64_t)kpairs;
+  }
 
   // ---- finalisation (:566-584)
   const int i = c.iter;

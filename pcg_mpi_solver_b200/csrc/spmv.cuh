@@ -207,8 +207,12 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
   // ---- segmented reduction: one group of LANES lanes per row, shuffle tree at the end
   constexpr int G = kSpmvBlock / LANES;
   const int gid = tid / LANES, gl = tid % LANES;
-  for (int i = gid; i < R; i += G) {
-    const int a = soff[i], e = soff[i + 1];
+  // NOTE: the trip count is uniform over the CTA (i0, not i, is tested) because the shuffle
+  // reduction below names all 32 lanes; lanes of a group past the last row just idle.
+  for (int i0 = 0; i0 < R; i0 += G) {
+    const int i = i0 + gid;
+    const bool live = i < R;
+    const int a = live ? soff[i] : 0, e = live ? soff[i + 1] : 0;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     int j = a + gl;
     for (; j + 3 * LANES < e; j += 4 * LANES) {
@@ -222,7 +226,7 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
     }
     for (; j < e; j += LANES) acc0 = fma(sval[j], __ldg(x + scol[j]), acc0);
     double acc = group_sum<LANES>((acc0 + acc1) + (acc2 + acc3));
-    if (gl == 0) srow[i] = acc;
+    if (live && gl == 0) srow[i] = acc;
   }
   __syncthreads();
 
@@ -290,10 +294,10 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   PCGB_CUDA(cudaStreamSynchronize(st));
   P.max_row = h_stats[0];
 
-  P.tile_items = env_int("PCGB_SPMV_TILE", 4096);
+  P.tile_items = env_int("PCGB_SPMV_TILE", 2048);  // 8 CTAs/SM: sweep in profiles/spmv_sweep_r1.txt
   if (P.tile_items < 256) P.tile_items = 256;
   const double avg = P.nrows ? (double)P.nnz / (double)P.nrows : 0.0;
-  int lanes = avg <= 6.0 ? 4 : avg <= 20.0 ? 8 : avg <= 96.0 ? 16 : 32;
+  int lanes = avg <= 12.0 ? 4 : avg <= 100.0 ? 8 : avg <= 200.0 ? 16 : 32;
   lanes = env_int("PCGB_SPMV_LANES", lanes);
   if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = 16;
   P.lanes = lanes;

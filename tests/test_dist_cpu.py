@@ -1,0 +1,71 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-rank logic: box partition, interface lists,
+ownership weights - the invariants the NCCL halo exchange relies on (partition_mesh.py:805-887)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _global_dofs(blk, local_dofs):
+    """Global dof ids of free-dof indices of a box."""
+    nxf = blk.ne[0] + 1 - blk.x_lo
+    node, d = np.divmod(np.asarray(local_dofs), 3)
+    lx = node % nxf + blk.x_lo
+    ly = (node // nxf) % (blk.ne[1] + 1)
+    lz = node // (nxf * (blk.ne[1] + 1))
+    gx, gy, gz = lx + blk.e0[0], ly + blk.e0[1], lz + blk.e0[2]
+    return 3 * ((gz * (blk.ng[1] + 1) + gy) * (blk.ng[0] + 1) + gx) + d
+
+
+def _worker(rank, world, port, ng, pgrid, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pcg_mpi_solver_b200.hexmesh import interface_lists, partition_blocks
+    blocks = partition_blocks(ng, pgrid)
+    blk = blocks[rank]
+    nbr, lists, w = interface_lists(blocks, rank)
+    # 1) both sides of every interface list the same global dofs in the same order
+    mine = {nb: _global_dofs(blk, l) for nb, l in zip(nbr, lists)}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    ok = True
+    for nb in nbr:
+        ok &= rank in everyone[nb] and np.array_equal(everyone[nb][rank], mine[nb])
+        ok &= bool(np.all(np.diff(mine[nb][::3]) > 0))  # ascending global node id
+    # 2) ownership weights partition the free dofs: sum over ranks = number of global free dofs
+    t = torch.tensor([float(w.sum())], dtype=torch.float64)
+    dist.all_reduce(t)
+    n_global = 3 * ng[0] * (ng[1] + 1) * (ng[2] + 1)
+    ok &= t.item() == n_global
+    # 3) a shared dof is owned (w = 1) by exactly the lowest rank holding it
+    owned = {int(g) for g in _global_dofs(blk, np.nonzero(w == 1)[0])}
+    all_owned = [None] * world
+    dist.all_gather_object(all_owned, owned)
+    if rank == 0:
+        union = set().union(*all_owned)
+        ok &= len(union) == sum(len(s) for s in all_owned) == n_global
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ng", [(2, (6, 5, 4)), (4, (8, 6, 3))])
+def test_interface_lists_gloo(world, ng):
+    from pcg_mpi_solver_b200.hexmesh import block_grid
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ng, block_grid(world), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

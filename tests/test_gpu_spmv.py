@@ -1,0 +1,133 @@
+"""GPU parity tests of the merge-path SpMV and the vector kernels against the CPU oracle
+(oracle/ref_pcg.py generators + scipy), called through the C ABI (libpcgb200.so via ctypes)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import ref_pcg as R
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-13  # per-entry |y - y_ref| <= RTOL * (|A| |x|)_i : fp64 summation-order noise only
+
+
+def _check_spmv(A, cuda, seed=0, **env):
+    import torch
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(A.shape[1])
+    y_ref = A @ x
+    scale = abs(A) @ np.abs(x) + 1e-300
+    M = CsrMatrix.from_scipy(A, device=cuda)
+    y = M.spmv(torch.from_numpy(x).to(cuda)).cpu().numpy()
+    err = np.abs(y - y_ref) / scale
+    assert err.max() <= RTOL, (err.max(), M.plan_info())
+    return M
+
+
+def test_spmv_poisson27_c1(cuda):
+    A = R.poisson27(32)  # config C1: n = 32768, nnz = 830584
+    assert A.nnz == 830584
+    M = _check_spmv(A, cuda)
+    assert M.plan_info()["snap"] == 1 and M.plan_info()["split_rows"] == 0
+
+
+def test_spmv_hex_box(cuda):
+    A = R.hex_box_csr((12, 10, 8), (0, 0, 0), (12, 10, 8))
+    _check_spmv(A, cuda)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("tma", [0, 1])
+def test_spmv_variants(cuda, monkeypatch, lanes, tma):
+    monkeypatch.setenv("PCGB_SPMV_LANES", str(lanes))
+    monkeypatch.setenv("PCGB_SPMV_TMA", str(tma))
+    A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
+    M = _check_spmv(A, cuda, seed=lanes)
+    info = M.plan_info()
+    assert info["lanes"] == lanes and info["tma"] == tma
+
+
+@pytest.mark.parametrize("tile", [256, 1024, 4096])
+def test_spmv_split_rows(cuda, monkeypatch, tile):
+    """Rows longer than a tile: pure merge-path split with the carry fix-up pass."""
+    monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
+    rng = np.random.default_rng(5)
+    n = 3000
+    A = sp.random(n, n, density=0.002, random_state=7, format="lil")
+    for r in (0, 17, 1500, n - 1):  # dense rows spanning many tiles
+        A[r, :] = rng.standard_normal(n)
+    A[5, :] = 0  # empty rows
+    A[6, :] = 0
+    A = A.tocsr()
+    M = _check_spmv(A, cuda)
+    info = M.plan_info()
+    assert info["snap"] == 0 and info["split_rows"] > 0
+
+
+def test_spmv_ragged_and_empty(cuda):
+    rng = np.random.default_rng(3)
+    n = 1237
+    A = sp.random(n, n, density=0.01, random_state=11, format="csr")
+    A.data[:] = rng.standard_normal(A.nnz)
+    _check_spmv(A, cuda)
+    # rectangular with trailing empty rows, nnz not a multiple of 4
+    B = sp.vstack([A[:100], sp.csr_matrix((7, n))]).tocsr()
+    _check_spmv(B, cuda)
+    # a single entry
+    C = sp.csr_matrix(([2.5], ([3], [2])), shape=(6, 6))
+    _check_spmv(C, cuda)
+    # no entries at all
+    Z = sp.csr_matrix((5, 5))
+    _check_spmv(Z, cuda)
+
+
+def test_spmv_int64_offsets(cuda):
+    import torch
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    A = R.hex_box_csr((6, 6, 6), (0, 0, 0), (6, 6, 6))
+    x = np.random.default_rng(1).standard_normal(A.shape[1])
+    M32 = CsrMatrix.from_scipy(A, device=cuda, index64=False)
+    M64 = CsrMatrix.from_scipy(A, device=cuda, index64=True)
+    xd = torch.from_numpy(x).to(cuda)
+    y32, y64 = M32.spmv(xd), M64.spmv(xd)
+    assert torch.equal(y32, y64)  # same plan -> bit-identical
+    assert M64.spmv_bytes() - M32.spmv_bytes() == 4 * (A.shape[0] + 1)
+
+
+def test_spmv_deterministic(cuda):
+    import torch
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    A = R.poisson27(20)
+    M = CsrMatrix.from_scipy(A, device=cuda)
+    x = torch.randn(A.shape[1], dtype=torch.float64, device=cuda)
+    y0 = M.spmv(x).clone()
+    for _ in range(5):
+        assert torch.equal(M.spmv(x), y0)
+
+
+def test_diag_and_vector_kernels(cuda):
+    import ctypes
+    import torch
+    from pcg_mpi_solver_b200 import _lib
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    A = R.hex_box_csr((5, 5, 5), (0, 0, 0), (5, 5, 5))
+    M = CsrMatrix.from_scipy(A, device=cuda)
+    np.testing.assert_allclose(M.diagonal().cpu().numpy(), A.diagonal(), rtol=1e-14)
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    n = 100003
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    w = (rng.random(n) > 0.3).astype(float)
+    ad, bd, wd = (torch.from_numpy(v).to(cuda) for v in (a, b, w))
+    out = torch.zeros(1, dtype=torch.float64, device=cuda)
+    _lib.check(lib.pcgb_dot_w(n, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(wd), _lib.ptr(out), _lib.stream_ptr()))
+    ref = np.dot(a, b * w)  # np.dot(a, b*w) as pcg_solver.py:462
+    assert abs(out.item() - ref) <= 1e-12 * np.dot(np.abs(a), np.abs(b) * w)
+    _lib.check(lib.pcgb_dot_w(n, _lib.ptr(ad), _lib.ptr(bd), None, _lib.ptr(out), _lib.stream_ptr()))
+    assert abs(out.item() - np.dot(a, b)) <= 1e-12 * np.dot(np.abs(a), np.abs(b))
+    yd = bd.clone()
+    _lib.check(lib.pcgb_axpby(n, 0.5, _lib.ptr(ad), -2.0, _lib.ptr(yd), _lib.stream_ptr()))
+    np.testing.assert_allclose(yd.cpu().numpy(), 0.5 * a - 2.0 * b, rtol=1e-15, atol=1e-15)
+    _lib.check(lib.pcgb_dot_w(0, None, None, None, _lib.ptr(out), _lib.stream_ptr()))  # empty input
+    assert out.item() == 0.0
