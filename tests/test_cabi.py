@@ -1,0 +1,61 @@
+"""CPU checks of the C ABI: the library loads without a GPU, exports every symbol include/pcgb200.h
+declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pcgb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcgb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pcg_mpi_solver_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pcgb200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.pcgb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    from pcg_mpi_solver_b200 import _lib
+    assert ctypes.sizeof(_lib.Options) == 48
+    assert ctypes.sizeof(_lib.Result) == 88
+    assert ctypes.sizeof(_lib.HexBox) == 36
+
+
+def test_no_cpu_fallback():
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pcg_mpi_solver_b200 import _lib, solve
+    from oracle import ref_pcg as R
+    lib = _lib.load()
+    assert lib.pcgb_device_count() == 0
+    h = ctypes.c_void_p()
+    rc = lib.pcgb_csr_create(1, 1, 0, 8, 0, None, None, None, ctypes.byref(h))
+    assert rc == -4 and b"no CPU fallback" in lib.pcgb_last_error()
+    A = R.poisson27(4)
+    with pytest.raises(_lib.PcgbError):
+        solve(A, np.ones(A.shape[0]), None, 1e-8, 10)
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "pcg_mpi_solver_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), (dirpath, f)
