@@ -105,7 +105,11 @@ class SubdomainData:
         """Upload A and build the halo plan: the `A` argument of solve() for this rank."""
         from .csr import CsrMatrix
         from .solver import SubdomainOperator
-        M = CsrMatrix.from_scipy(self.A, device=device)
+        if self.A is not None:
+            M = CsrMatrix.from_scipy(self.A, device=device)
+        else:  # assemble on the device straight from the pattern groups
+            rowptr, col, val = assemble_csr_device(self, device)
+            M = CsrMatrix(rowptr, col, val, (self.n, self.n))
         return SubdomainOperator(M, comm, self.nbr, self.ovrlp, self.weights, n_global=self.n_global_eff)
 
 
@@ -127,7 +131,7 @@ def _assemble(groups, ndof: int) -> sp.csr_matrix:
     return K
 
 
-def build_subdomains(model: MdfModel, elepart: np.ndarray, nparts: int, assemble: bool = True, delta: float = 1.0):
+def build_subdomains(model: MdfModel, elepart: np.ndarray, nparts: int, assemble=True, delta: float = 1.0):
     """The partition_mesh.py stage for all parts (single process; the reference's MPGSize = N path)."""
     elepart = np.asarray(elepart)
     subs = []
@@ -176,27 +180,82 @@ def build_subdomains(model: MdfModel, elepart: np.ndarray, nparts: int, assemble
             p.ovrlp.append(eff_pos[dofs[is_eff[dofs]]].astype(np.int64))
             if p.id > q.id:                                                # :885-887
                 p.weights_full[dofs] = 0.0
-    # ---- operator, right-hand side (updateBC, pcg_solver.py:226-238)
-    if assemble:
-        fdi_glob = np.zeros(model.n_dof)
-        any_ud = bool(np.any(model.Ud != 0))
+    # ---- right-hand side (updateBC, pcg_solver.py:226-238): Fext = F*delta - K (Ud*delta), interface-summed
+    fdi_glob = np.zeros(model.n_dof)
+    any_ud = bool(np.any(model.Ud != 0))
+    for p in subs:
+        p.udi = p.Ud * delta
+        if any_ud:
+            fdi_glob[p.dof_vector] += _ebe_matvec(p.groups, p.udi, p.ndof)  # the sum over parts IS the interface sum
+    for p in subs:
+        fext = p.F * delta - fdi_glob[p.dof_vector]
+        p.b = fext[p.loc_dof_eff]
+    # ---- operator
+    if assemble in (True, "host"):
         for p in subs:
             K = _assemble(p.groups, p.ndof)
-            p.udi = p.Ud * delta
-            if any_ud:
-                fdi_glob[p.dof_vector] += K @ p.udi                        # local product; the sum over parts is the interface sum
             p.A = K[p.loc_dof_eff][:, p.loc_dof_eff].tocsr()
             p.A.sort_indices()
-        for p in subs:
-            fext = p.F * delta - fdi_glob[p.dof_vector]
-            p.b = fext[p.loc_dof_eff]
     return subs
 
 
-def partition_mesh(model, nparts: int, elepart: np.ndarray | None = None, assemble: bool = True, ncommon: int = 1):
+def _ebe_matvec(groups, x_full, ndof):
+    """y = K_i x on all local dofs, element by element (only used once, for the Dirichlet term of the RHS)."""
+    y = np.zeros(ndof)
+    for g in groups:
+        s = np.where(g.sign, -1.0, 1.0)
+        v = s * (g.ke @ (g.ck * (s * x_full[g.loc_dof])))
+        y += np.bincount(g.loc_dof.ravel(), weights=v.ravel(), minlength=ndof)
+    return y
+
+
+def assemble_csr_device(sub: SubdomainData, device="cuda", chunk_entries: int = 1 << 27):
+    """K_i[Eff,Eff] assembled ON THE DEVICE from the pattern groups: expand to COO keys, stable sort,
+    segmented sum (deterministic), compress to CSR.  Set-up code (torch tensor ops as plumbing; the hot path
+    starts at the CSR arrays).  Returns (rowptr int32/int64, col int32, val float64) CUDA tensors."""
+    import torch
+    n = sub.n
+    eff_map = torch.full((sub.ndof,), -1, dtype=torch.int64, device=device)
+    eff_map[torch.from_numpy(sub.loc_dof_eff).to(device)] = torch.arange(n, device=device)
+    keys, vals = [], []
+    for g in sub.groups:
+        nd, ne = g.loc_dof.shape
+        ke = torch.from_numpy(g.ke).to(device)
+        step = max(1, chunk_entries // (nd * nd))
+        for e0 in range(0, ne, step):
+            sl = slice(e0, min(ne, e0 + step))
+            r = eff_map[torch.from_numpy(g.loc_dof[:, sl]).to(device)]                       # (nd, m)
+            s = torch.where(torch.from_numpy(g.sign[:, sl]).to(device), -1.0, 1.0).to(torch.float64)
+            ck = torch.from_numpy(g.ck[sl]).to(device)
+            v = (s[:, None, :] * s[None, :, :]) * ke[:, :, None] * ck[None, None, :]          # (nd, nd, m)
+            key = r[:, None, :] * n + r[None, :, :]
+            ok = (r[:, None, :] >= 0) & (r[None, :, :] >= 0)
+            keys.append(key[ok])
+            vals.append(v[ok])
+    key = torch.cat(keys)
+    val = torch.cat(vals)
+    del keys, vals
+    key, perm = torch.sort(key, stable=True)
+    val = val[perm]
+    del perm
+    ukey, counts = torch.unique_consecutive(key, return_counts=True)
+    del key
+    sval = torch.segment_reduce(val, "sum", lengths=counts)
+    rows = ukey // n
+    col = (ukey - rows * n).to(torch.int32)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    if sval.numel() < 2**31:
+        rowptr = rowptr.to(torch.int32)
+    return rowptr, col, sval.contiguous()
+
+
+def partition_mesh(model, nparts: int, elepart: np.ndarray | None = None, assemble=True, ncommon: int = 1):
     """run_metis.py + partition_mesh.py as one call.
 
     model: MdfModel, or a path to `<model>.zip` / an unpacked MDF directory.
+    assemble: True/"host" = scipy COO->CSR on the host (small models, CPU tests); False/"device" = leave A
+    unset, SubdomainData.to_operator() then assembles on the GPU (88 s -> ~1 s for data/concrete.zip).
     Returns the list of SubdomainData, one per part (part i is solved by rank / GPU i, pcg_solver.py:91).
     """
     if not isinstance(model, MdfModel):

@@ -34,3 +34,24 @@ def test_multi_gpu_matches_oracle(cuda, tmp_path, world, graph):
     assert res["copy_mismatch"] <= 1e-12      # shared dofs stay consistent across ranks
     assert res["weight_sum"] == res["n_global"]  # ownership weights partition the free dofs
     assert all(tuple(i) == tuple(res["all_infos"][0]) for i in res["all_infos"])  # every rank agrees
+
+
+def test_concrete_8gpu_matches_reference_8rank_run(cuda, tmp_path):
+    """Config C4: concrete.zip, 8-way METIS, one part per GPU, vs the reference's own 8-rank run (golden G6)."""
+    import torch
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    root = os.path.dirname(HERE)
+    zp = os.path.join(root, "oracle", "_ref", "concrete.zip")
+    if not os.path.exists(zp):
+        pytest.skip("data/concrete.zip not staged")
+    out = tmp_path / "concrete8.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=8", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(HERE, "mgpu_worker.py"), str(out), "concrete", zp]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:]
+    res = json.loads(out.read_text())
+    ref = res["ref"]
+    assert res["flag"] == ref["Flag"] == 0 and abs(res["iters"] - ref["Iter"]) <= 2 and res["relres"] <= 1e-7
+    assert abs(res["norm_u"] - ref["norm2_U"]) <= 1e-7 * ref["norm2_U"]
+    assert res["sample_err"] <= 1e-6
