@@ -60,8 +60,12 @@ int pcgb_spmv(pcgb_csr_t A, const double *d_x, double *d_y, void *stream);
 int pcgb_csr_diag(pcgb_csr_t A, double *d_diag, void *stream);
 /* Algorithmic bytes of one SpMV: 12*nnz + R*(nrows+1) + 8*ncols + 8*nrows. */
 int64_t pcgb_spmv_bytes(pcgb_csr_t A);
-/* plan introspection for tests / DESIGN.md: tiles, lanes per row, split-row count, smem bytes */
-int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[8]);
+/* Bytes the selected kernel really streams from HBM (the staged-x kernel reads 16-bit local column
+ * indices: 10 B per non-zero instead of 12). */
+int64_t pcgb_spmv_stream_bytes(pcgb_csr_t A);
+/* plan introspection for tests / DESIGN.md: tiles, tile items, lanes, snap, split rows, smem bytes,
+ * max row, tma, staged, x windows, staged doubles per tile (cap), max windows per tile */
+int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[12]);
 
 /* ---------------------------------------------------------------- vector kernels (a4-a10)
  * out[0] = sum_i a[i]*b[i]*w[i]   (w may be NULL = all ones).  np.dot(a, b*w) of

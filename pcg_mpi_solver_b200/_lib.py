@@ -47,6 +47,7 @@ SIGNATURES = {
     "pcgb_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_csr_diag": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pcgb_spmv_bytes": (c_int64, [c_void_p]),
+    "pcgb_spmv_stream_bytes": (c_int64, [c_void_p]),
     "pcgb_csr_plan_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "pcgb_dot_w": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_axpby": (c_int, [c_int64, c_double, c_void_p, c_double, c_void_p, c_void_p]),

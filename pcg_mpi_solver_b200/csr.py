@@ -71,10 +71,15 @@ class CsrMatrix:
         """Algorithmic bytes of one SpMV: 12 nnz + R (n+1) + 8 ncols + 8 nrows."""
         return int(_lib.load().pcgb_spmv_bytes(self._h))
 
+    def stream_bytes(self) -> int:
+        """HBM bytes the selected kernel streams per SpMV (10 B/nnz for the staged-x kernel)."""
+        return int(_lib.load().pcgb_spmv_stream_bytes(self._h))
+
     def plan_info(self) -> dict:
-        info = (ctypes.c_int64 * 8)()
+        info = (ctypes.c_int64 * 12)()
         _lib.check(_lib.load().pcgb_csr_plan_info(self._h, info))
-        keys = ["ntiles", "tile_items", "lanes", "snap", "split_rows", "smem_bytes", "max_row", "tma"]
+        keys = ["ntiles", "tile_items", "lanes", "snap", "split_rows", "smem_bytes", "max_row", "tma", "staged", "x_windows",
+                "x_cap", "max_windows_per_tile"]
         return dict(zip(keys, [int(v) for v in info]))
 
     def to_scipy(self):

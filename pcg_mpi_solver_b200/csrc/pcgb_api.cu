@@ -111,11 +111,21 @@ int64_t pcgb_spmv_bytes(pcgb_csr_t A) {
   return 12 * P.nnz + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows;
 }
 
-int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[8]) {
+/* bytes the selected kernel actually streams from HBM per SpMV (staged-x: 10 B per non-zero + window tables) */
+int64_t pcgb_spmv_stream_bytes(pcgb_csr_t A) {
+  if (!A) return 0;
+  const CsrPlan &P = A->P;
+  const int64_t per = P.staged ? 10 : 12;
+  return per * P.nnz + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows + (P.staged ? 8 * P.nwin + 8 * (int64_t)P.ntiles : 0) + 12 * (int64_t)P.ntiles;
+}
+
+int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[12]) {
   if (!A || !info) return fail(PCGB_ERR_ARG, "pcgb_csr_plan_info: null argument");
   const CsrPlan &P = A->P;
   info[0] = P.ntiles; info[1] = P.tile_items; info[2] = P.lanes; info[3] = P.snap ? 1 : 0;
-  info[4] = P.nfix; info[5] = P.smem_bytes; info[6] = P.max_row; info[7] = P.use_tma ? 1 : 0;
+  info[4] = P.nfix; info[5] = P.staged ? P.smem_staged : P.smem_bytes; info[6] = P.max_row; info[7] = P.use_tma ? 1 : 0;
+  info[8] = P.persist ? 2 : (P.staged ? 1 : 0); info[9] = P.nwin; info[10] = P.cap_x; info[11] = P.max_nw;
+  if (P.persist) info[5] = P.smem_persist;
   return PCGB_OK;
 }
 
@@ -379,7 +389,7 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   // UNASSEMBLED local product, whose rank sum equals the reference's weighted dot of the assembled q
   // (p is consistent on shared dofs and K = sum of the subdomain matrices); see DESIGN.md.
   const double *pq_src = P.dot_partials;
-  int pq_cnt = P.ntiles;
+  int pq_cnt = P.persist ? P.grid_persist : P.ntiles;
   if (pq_cnt > 8192) {
     const int sb = (pq_cnt + 4095) / 4096;
     k_stage_reduce<<<sb, 256, 0, st>>>(P.dot_partials, pq_cnt, s->stage);

@@ -23,6 +23,21 @@
 namespace pcgb {
 
 constexpr int kSpmvBlock = 256;
+constexpr int kAlignMask = 7;      // tiles are staged from an 8-element aligned start
+constexpr int kMaxRuns = 2048;     // staged-x plan: column runs per tile
+constexpr int kMaxWin = 256;       // staged-x plan: x windows per tile
+constexpr int kMaxXLen = 6144;     // staged-x plan: doubles of x staged per tile (48 KB)
+
+// per-tile descriptor of the persistent kernel: everything a producer warp needs in one 32-byte load
+struct __align__(16) TileDesc {
+  int64_t k0;   // first non-zero of the tile
+  int cnt;      // non-zeros in the tile
+  int r0;       // first row
+  int R;        // rows with a segment here (incl. a partial last row); bit 31 = first row is a continuation
+  int wb;       // first x window
+  int nw;       // x windows
+  int xlen;     // staged doubles of x
+};
 
 struct CsrPlan {
   int64_t nrows = 0, ncols = 0, nnz = 0;
@@ -40,6 +55,19 @@ struct CsrPlan {
   int nfix = 0;                  // rows that span more than one tile
   int *fix_row = nullptr, *fix_first = nullptr, *fix_cnt = nullptr;
   double *dot_partials = nullptr;  // [ntiles]  fused  x.y  partials
+  // staged-x variant (k_spmv_staged): x windows per tile + 16-bit local column indices
+  bool staged = false;
+  uint16_t *lidx = nullptr;        // [nnz + 16]  position of col[k] inside the tile's staged x buffer
+  int *tile_win = nullptr;         // [ntiles+1]  window range of each tile
+  int *win_start = nullptr;        // [nwin]      first column of the window
+  int *win_off = nullptr;          // [nwin]      offset of the window inside the staged buffer
+  int *tile_xlen = nullptr;        // [ntiles]    staged doubles per tile
+  int cap_x = 0, max_nw = 0, smem_staged = 0;
+  int64_t nwin = 0;
+  // persistent pipelined variant (k_spmv_persist)
+  bool persist = false;
+  struct TileDesc *tile_desc = nullptr;  // [ntiles]
+  int stages = 0, stage_bytes = 0, smem_persist = 0, grid_persist = 0;
 };
 
 // ------------------------------------------------------------------ PTX wrappers (TMA bulk copy)
@@ -129,7 +157,7 @@ __global__ void k_tile_stats(const RP *__restrict__ rowptr, const int *__restric
   if (b >= ntiles) return;
   int64_t k0 = tile_k[b], k1 = tile_k[b + 1];
   int r0 = tile_row[b], r1 = tile_row[b + 1];
-  int cnt = (int)(k1 - (k0 & ~(int64_t)3));
+  int cnt = (int)(k1 - (k0 & ~(int64_t)kAlignMask));
   atomicMax(max_cnt, cnt);
   atomicMax(max_rows, r1 - r0 + 1);
   head_flag[b] = (int64_t)rowptr[r0] < k0 ? 1 : 0;
@@ -155,7 +183,7 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
   const int b = blockIdx.x;
   const int r0 = tile_row[b], r1 = tile_row[b + 1];
   const int64_t k0 = tile_k[b], k1 = tile_k[b + 1];
-  const int64_t ka = k0 & ~(int64_t)3;  // 16-byte aligned start of the staged window
+  const int64_t ka = k0 & ~(int64_t)kAlignMask;  // aligned start of the staged window (16 B for every array)
   const int k0l = (int)(k0 - ka), k1l = (int)(k1 - ka);
   const bool tail = (r1 < nrows) && (k1 > (int64_t)rowptr[r1]);
   const int R = r1 - r0 + (tail ? 1 : 0);  // rows that own at least a (possibly empty) segment here
@@ -166,8 +194,8 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
     if (tid == 0) {
       mbar_init(&bar, 1);
       mbar_fence_init();
-      int64_t kend = (k1 + 3) & ~(int64_t)3;
-      const int64_t lim = nnz & ~(int64_t)3;
+      int64_t kend = (k1 + kAlignMask) & ~(int64_t)kAlignMask;
+      const int64_t lim = nnz & ~(int64_t)kAlignMask;
       if (kend > lim) kend = lim;
       const int nb = (int)(kend - ka);
       if (nb > 0) {
@@ -179,11 +207,11 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
         mbar_arrive(&bar);
       }
     }
-    // the (at most 3) elements beyond the last full 16-byte quad of the arrays
+    // the (at most 7) elements beyond the last full aligned group of the arrays
     {
-      const int64_t lim = nnz & ~(int64_t)3;
+      const int64_t lim = nnz & ~(int64_t)kAlignMask;
       int64_t kt = (lim > ka ? lim : ka) + tid;
-      if (tid < 4 && kt >= lim && kt < k1) {
+      if (tid <= kAlignMask && kt >= lim && kt < k1) {
         sval[kt - ka] = val[kt];
         scol[kt - ka] = col[kt];
       }
@@ -243,6 +271,426 @@ k_spmv_merge(const RP *__restrict__ rowptr, const int *__restrict__ col, const d
     double v[1] = {d};
     block_sum<1, kSpmvBlock>(v, red);
     if (tid == 0) dot_partials[b] = v[0];
+  }
+}
+
+
+// ------------------------------------------------------------------ staged-x variant: plan
+// One CTA per tile.  Finds the maximal runs of consecutive columns in the tile, sorts them by first
+// column, merges them (gap tolerance `gap`) into x windows, and rewrites every column index as a 16-bit
+// position inside the concatenation of the tile's windows.
+__global__ void __launch_bounds__(256)
+k_plan_windows(const int *__restrict__ col, const int64_t *__restrict__ tile_k, int cap, int gap, int pass,
+               const int *__restrict__ tile_win, uint16_t *__restrict__ lidx, int *__restrict__ win_start,
+               int *__restrict__ win_off, int *__restrict__ tile_nw, int *__restrict__ tile_xlen, int *__restrict__ fail) {
+  // pass 1: only count windows / staged length per tile;  pass 2: write the windows at tile_win[b] and lidx
+  extern __shared__ int sm[];
+  int *scol = sm;                 // cap
+  int *rkey = scol + cap;         // kMaxRuns   first column of a run (sort key)
+  int *rlen = rkey + kMaxRuns;    // kMaxRuns   run length
+  int *rpos = rlen + kMaxRuns;    // kMaxRuns   position of the run head inside the tile
+  int *wst = rpos + kMaxRuns;     // kMaxWin
+  int *wof = wst + kMaxWin;       // kMaxWin + 1
+  __shared__ int s_scan[256];
+  __shared__ int s_nruns, s_nw, s_fail;
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int64_t k0 = tile_k[b], k1 = tile_k[b + 1];
+  const int cnt = (int)(k1 - k0);
+  if (tid == 0) { s_fail = 0; s_nw = 0; }
+  for (int j = tid; j < cnt; j += 256) scol[j] = col[k0 + j];
+  __syncthreads();
+  // ---- run heads: one contiguous chunk per thread, exclusive scan of the head counts over the CTA
+  const int per = (cnt + 255) / 256;
+  const int lo = min(cnt, tid * per), hi = min(cnt, lo + per);
+  int mine = 0;
+  for (int j = lo; j < hi; ++j) mine += (j == 0 || scol[j] != scol[j - 1] + 1) ? 1 : 0;
+  s_scan[tid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int t = 0; t < 256; ++t) { const int v = s_scan[t]; s_scan[t] = acc; acc += v; }
+    s_nruns = acc;
+    if (acc > kMaxRuns) s_fail = 1;
+  }
+  __syncthreads();
+  const int nruns = s_nruns;
+  if (s_fail) {
+    if (tid == 0) { atomicExch(fail, 1); if (pass == 1) { tile_nw[b] = 0; tile_xlen[b] = 0; } }
+    return;
+  }
+  {
+    int o = s_scan[tid];
+    for (int j = lo; j < hi; ++j)
+      if (j == 0 || scol[j] != scol[j - 1] + 1) { rkey[o] = scol[j]; rpos[o] = j; ++o; }
+  }
+  __syncthreads();
+  for (int i = tid; i < nruns; i += 256) rlen[i] = ((i + 1 < nruns) ? rpos[i + 1] : cnt) - rpos[i];
+  int np2 = 1;
+  while (np2 < nruns) np2 <<= 1;
+  for (int i = nruns + tid; i < np2; i += 256) { rkey[i] = INT32_MAX; rlen[i] = 0; }
+  __syncthreads();
+  // ---- bitonic sort of (rkey, rlen) by rkey
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += 256) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const int a = rkey[i], c = rkey[l];
+          if ((a > c) == up) {
+            rkey[i] = c; rkey[l] = a;
+            const int t = rlen[i]; rlen[i] = rlen[l]; rlen[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  // ---- merge the sorted runs into windows (sequential: a few hundred steps)
+  if (tid == 0) {
+    int nw = 0, xlen = 0, cs = 0, ce = -1;
+    bool bad = false;
+    for (int i = 0; i < nruns; ++i) {
+      const int s = rkey[i], e = s + rlen[i];
+      if (nw == 0 || s > ce + gap) {
+        if (nw > 0) xlen += ce - cs;
+        if (nw >= kMaxWin) { bad = true; break; }
+        wst[nw] = s; wof[nw] = xlen; ++nw;
+        cs = s; ce = e;
+      } else if (e > ce) ce = e;
+    }
+    if (nw > 0) xlen += ce - cs;
+    wof[nw] = xlen;
+    if (bad || xlen > kMaxXLen) { s_fail = 1; atomicExch(fail, 1); nw = 0; xlen = 0; }
+    s_nw = nw;
+    if (pass == 1) { tile_nw[b] = nw; tile_xlen[b] = xlen; }
+  }
+  __syncthreads();
+  if (s_fail || pass == 1) return;
+  const int nw = s_nw, base = tile_win[b];
+  for (int w = tid; w < nw; w += 256) { win_start[base + w] = wst[w]; win_off[base + w] = wof[w]; }
+  // ---- local index of every entry: window by binary search over the window starts
+  for (int j = tid; j < cnt; j += 256) {
+    const int c = scol[j];
+    int a = 0, z = nw - 1;
+    while (a < z) {
+      const int m = (a + z + 1) >> 1;
+      if (wst[m] <= c) a = m; else z = m - 1;
+    }
+    lidx[k0 + j] = (uint16_t)(wof[a] + (c - wst[a]));
+  }
+}
+
+// ------------------------------------------------------------------ staged-x variant: the kernel
+// Same tile / row structure as k_spmv_merge, but (i) the gather of x goes to SHARED memory: the tile's x
+// windows are copied in once, coalesced; (ii) the column stream is the 16-bit local index, so the kernel
+// reads 10 bytes per non-zero from HBM instead of 12 and the 4-byte col array is not touched at all.
+template <int LANES, bool DOT, typename RP>
+__global__ void __launch_bounds__(kSpmvBlock)
+k_spmv_staged(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx, const double *__restrict__ val,
+              const double *__restrict__ x, double *__restrict__ y, const int *__restrict__ tile_row,
+              const int64_t *__restrict__ tile_k, const int *__restrict__ tile_win, const int *__restrict__ win_start,
+              const int *__restrict__ win_off, const int *__restrict__ tile_xlen, int64_t nrows, int64_t nnz, int cap_nnz,
+              int cap_rows, int cap_x, double *__restrict__ carry, double *__restrict__ dot_partials,
+              const int *__restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sval = reinterpret_cast<double *>(smem_raw);               // cap_nnz
+  double *sx = sval + cap_nnz;                                       // cap_x
+  double *srow = sx + cap_x;                                         // cap_rows
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(srow + cap_rows);    // cap_nnz
+  int *soff = reinterpret_cast<int *>(sidx + cap_nnz);               // cap_rows + 1
+  __shared__ uint64_t bar;
+  __shared__ double red[32];
+
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int r0 = tile_row[b], r1 = tile_row[b + 1];
+  const int64_t k0 = tile_k[b], k1 = tile_k[b + 1];
+  const int64_t ka = k0 & ~(int64_t)kAlignMask;
+  const int k0l = (int)(k0 - ka), k1l = (int)(k1 - ka);
+  const bool tail = (r1 < nrows) && (k1 > (int64_t)rowptr[r1]);
+  const int R = r1 - r0 + (tail ? 1 : 0);
+  const bool head = (R > 0) && ((int64_t)rowptr[r0] < k0);
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    int64_t kend = (k1 + kAlignMask) & ~(int64_t)kAlignMask;
+    const int64_t lim = nnz & ~(int64_t)kAlignMask;
+    if (kend > lim) kend = lim;
+    const int nb = (int)(kend - ka);
+    if (nb > 0) {
+      const uint64_t pol = l2_evict_first_policy();
+      mbar_expect_tx(&bar, (uint32_t)nb * 10u);
+      bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &bar, pol);
+      bulk_g2s(sidx, lidx + ka, (uint32_t)nb * 2u, &bar, pol);
+    } else {
+      mbar_arrive(&bar);
+    }
+  }
+  {
+    const int64_t lim = nnz & ~(int64_t)kAlignMask;
+    int64_t kt = (lim > ka ? lim : ka) + tid;
+    if (tid <= kAlignMask && kt >= lim && kt < k1) {
+      sval[kt - ka] = val[kt];
+      sidx[kt - ka] = lidx[kt];
+    }
+  }
+  // ---- x windows -> shared memory (one warp per window, coalesced)
+  {
+    const int wb = tile_win[b], nw = tile_win[b + 1] - wb, xlen = tile_xlen[b];
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int w = warp; w < nw; w += kSpmvBlock / 32) {
+      const int s = win_start[wb + w], o = win_off[wb + w];
+      const int len = ((w + 1 < nw) ? win_off[wb + w + 1] : xlen) - o;
+      for (int t = lane; t < len; t += 32) sx[o + t] = __ldg(x + s + t);
+    }
+  }
+  for (int i = tid; i <= R; i += kSpmvBlock) {
+    int64_t v = (int64_t)rowptr[r0 + i] - ka;
+    v = v < k0l ? k0l : (v > k1l ? k1l : v);
+    soff[i] = (int)v;
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  constexpr int G = kSpmvBlock / LANES;
+  const int gid = tid / LANES, gl = tid % LANES;
+  for (int i0 = 0; i0 < R; i0 += G) {  // CTA-uniform trip count (full-mask shuffles below)
+    const int i = i0 + gid;
+    const bool live = i < R;
+    const int a = live ? soff[i] : 0, e = live ? soff[i + 1] : 0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int j = a + gl;
+    for (; j + 3 * LANES < e; j += 4 * LANES) {
+      const double x0 = sx[sidx[j]], x1 = sx[sidx[j + LANES]], x2 = sx[sidx[j + 2 * LANES]], x3 = sx[sidx[j + 3 * LANES]];
+      acc0 = fma(sval[j], x0, acc0);
+      acc1 = fma(sval[j + LANES], x1, acc1);
+      acc2 = fma(sval[j + 2 * LANES], x2, acc2);
+      acc3 = fma(sval[j + 3 * LANES], x3, acc3);
+    }
+    for (; j < e; j += LANES) acc0 = fma(sval[j], sx[sidx[j]], acc0);
+    double acc = group_sum<LANES>((acc0 + acc1) + (acc2 + acc3));
+    if (live && gl == 0) srow[i] = acc;
+  }
+  __syncthreads();
+
+  double d = 0.0;
+  for (int i = tid; i < R; i += kSpmvBlock) {
+    const double s = srow[i];
+    const int r = r0 + i;
+    if (i == 0 && head) carry[b] = s;
+    else y[r] = s;
+    if (DOT) d = fma(s, __ldg(x + r), d);
+  }
+  if (DOT) {
+    double v[1] = {d};
+    block_sum<1, kSpmvBlock>(v, red);
+    if (tid == 0) dot_partials[b] = v[0];
+  }
+}
+
+
+// ------------------------------------------------------------------ persistent, warp-specialised, pipelined variant
+// One CTA = 8 consumer warps + kProd producer warps, kept resident (grid = SMs x CTAs/SM), looping over
+// tiles c, c+grid, ... through a ring of `stages` shared-memory stages guarded by full/empty mbarriers:
+//   producer warp (stage s):  wait empty[s] -> TMA bulk copies of val / 16-bit lidx -> copy the tile's x
+//                             windows, x[r0..r0+R) and clamped row offsets into the stage -> arrive full[s]
+//   consumer warps:           wait full[s] -> sub-warp groups reduce the rows out of shared memory,
+//                             group leaders write y (and accumulate x.y) -> arrive empty[s]
+// Consumers never wait on a global load; HBM streaming is entirely asynchronous (UBLKCP) and `stages` tiles deep.
+constexpr int kProd = 4;          // producer warps = stages served round-robin
+constexpr int kConsWarps = 8;
+constexpr int kPersistThreads = (kConsWarps + kProd) * 32;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <typename RP>
+__global__ void k_build_desc(const RP *__restrict__ rowptr, const int *__restrict__ tile_row, const int64_t *__restrict__ tile_k,
+                             const int *__restrict__ tile_win, const int *__restrict__ tile_xlen, int ntiles, int64_t nrows,
+                             TileDesc *__restrict__ desc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ntiles) return;
+  const int r0 = tile_row[b], r1 = tile_row[b + 1];
+  const int64_t k0 = tile_k[b], k1 = tile_k[b + 1];
+  const bool tail = (r1 < nrows) && (k1 > (int64_t)rowptr[r1]);
+  const int R = r1 - r0 + (tail ? 1 : 0);
+  const bool head = (R > 0) && ((int64_t)rowptr[r0] < k0);
+  TileDesc d;
+  d.k0 = k0; d.cnt = (int)(k1 - k0); d.r0 = r0; d.R = R | (head ? (int)0x80000000 : 0);
+  d.wb = tile_win[b]; d.nw = tile_win[b + 1] - tile_win[b]; d.xlen = tile_xlen[b];
+  desc[b] = d;
+}
+
+// cp.async (LDGSTS): asynchronous global -> shared copies issued by the producer lanes; their completion is
+// reported to the stage's full barrier with cp.async.mbarrier.arrive.noinc (one arrival per lane).
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int LANES, bool DOT, typename RP>
+__global__ void __launch_bounds__(kPersistThreads)
+k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx, const double *__restrict__ val,
+               const double *__restrict__ x, double *__restrict__ y, const TileDesc *__restrict__ desc,
+               const int *__restrict__ win_start, const int *__restrict__ win_off, int ntiles, int64_t nnz, int cap_nnz,
+               int cap_rows, int cap_x, int stages, int stage_bytes, double *__restrict__ carry,
+               double *__restrict__ dot_partials, const int *__restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8];
+  __shared__ double red[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    // full: 1 (TMA expect_tx arrive) + 32 (cp.async completion, one per producer lane) + 1 (producer's own stores)
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 34); mbar_init(&empty_bar[s], kConsWarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | sxr[cap_rows] f64 | srp[cap_rows+2] i64 | sidx[cap_nnz] u16 | meta[8] i32
+  const size_t off_sx = (size_t)cap_nnz * 8, off_sxr = off_sx + (size_t)cap_x * 8, off_srp = off_sxr + (size_t)cap_rows * 8;
+  const size_t off_sidx = off_srp + (size_t)(cap_rows + 2) * 8, off_meta = off_sidx + (size_t)cap_nnz * 2;
+
+  if (warp >= kConsWarps) {
+    // ================= producer warp p: tiles it = p, p + kProd, ... (stage = it % stages, stages % kProd == 0)
+    const int p = warp - kConsWarps;
+    const uint64_t pol = l2_evict_first_policy();
+    for (int it = p;; it += kProd) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      if (tile >= ntiles) break;
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)((it / stages) & 1);
+      const int4 *dp = reinterpret_cast<const int4 *>(desc + tile);  // one 32-byte descriptor, broadcast load
+      const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+      const int64_t k0 = ((int64_t)(uint32_t)d0.x) | ((int64_t)d0.y << 32);
+      const int cnt = d0.z, r0 = d0.w, Rraw = d1.x, wb = d1.y, nw = d1.z, xlen = d1.w;
+      const int R = Rraw & 0x7fffffff;
+      unsigned char *base = smem_raw + (size_t)s * stage_bytes;
+      double *sval = reinterpret_cast<double *>(base);
+      double *sx = reinterpret_cast<double *>(base + off_sx);
+      double *sxr = reinterpret_cast<double *>(base + off_sxr);
+      RP *srp = reinterpret_cast<RP *>(base + off_srp);
+      uint16_t *sidx = reinterpret_cast<uint16_t *>(base + off_sidx);
+      int *meta = reinterpret_cast<int *>(base + off_meta);
+      const int64_t k1 = k0 + cnt;
+      const int64_t ka = k0 & ~(int64_t)kAlignMask;
+      // window descriptors do not depend on the stage being free: fetch them while waiting
+      int ws = 0, wo = 0;
+      if (lane < nw) { ws = __ldg(win_start + wb + lane); wo = __ldg(win_off + wb + lane); }
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (lane == 0) {
+        int64_t kend = (k1 + kAlignMask) & ~(int64_t)kAlignMask;
+        const int64_t lim = nnz & ~(int64_t)kAlignMask;
+        if (kend > lim) kend = lim;
+        const int nb = (int)(kend - ka);
+        if (nb > 0) {
+          mbar_expect_tx(&full_bar[s], (uint32_t)nb * 10u);
+          bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &full_bar[s], pol);
+          bulk_g2s(sidx, lidx + ka, (uint32_t)nb * 2u, &full_bar[s], pol);
+        } else {
+          mbar_arrive(&full_bar[s]);
+        }
+        meta[0] = r0; meta[1] = Rraw; meta[2] = tile; meta[3] = cnt;
+        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32);
+      }
+      {
+        const int64_t lim = nnz & ~(int64_t)kAlignMask;
+        const int64_t kt = (lim > ka ? lim : ka) + lane;
+        if (lane <= kAlignMask && kt >= lim && kt < k1) { sval[kt - ka] = val[kt]; sidx[kt - ka] = lidx[kt]; }
+      }
+      // raw row offsets and the x entries of the tile's own rows: asynchronous copies
+      for (int i = lane; i <= R; i += 32) cp_async<sizeof(RP)>(srp + i, rowptr + r0 + i);
+      if (DOT) for (int i = lane; i < R; i += 32) cp_async<8>(sxr + i, x + r0 + i);
+      // x windows (descriptor w broadcast from the lane that fetched it)
+      for (int w0 = 0; w0 < nw; w0 += 32) {
+        if (w0 > 0) {
+          ws = 0; wo = 0;
+          if (w0 + lane < nw) { ws = __ldg(win_start + wb + w0 + lane); wo = __ldg(win_off + wb + w0 + lane); }
+        }
+        const int nwc = min(32, nw - w0);
+        const int wo_next = (w0 + nwc < nw) ? __ldg(win_off + wb + w0 + nwc) : xlen;
+        for (int w = 0; w < nwc; ++w) {
+          const int s0 = __shfl_sync(0xffffffffu, ws, w), o0 = __shfl_sync(0xffffffffu, wo, w);
+          const int o1n = __shfl_sync(0xffffffffu, wo, (w + 1) & 31);
+          const int len = ((w + 1 < nwc) ? o1n : wo_next) - o0;
+          for (int t = lane; t < len; t += 32) cp_async<8>(sx + o0 + t, x + s0 + t);
+        }
+      }
+      cp_async_arrive_noinc(&full_bar[s]);       // fires when this lane's cp.async copies have landed
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);  // release: meta / tail stores of the warp
+    }
+    return;
+  }
+
+  // ================= consumer warps
+  constexpr int G = (kConsWarps * 32) / LANES;
+  const int gid = tid / LANES, gl = tid % LANES;
+  double dsum = 0.0;
+  for (int it = 0;; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) break;
+    const int s = it % stages;
+    const uint32_t ph = (uint32_t)((it / stages) & 1);
+    const unsigned char *base = smem_raw + (size_t)s * stage_bytes;
+    const double *sval = reinterpret_cast<const double *>(base);
+    const double *sx = reinterpret_cast<const double *>(base + off_sx);
+    const double *sxr = reinterpret_cast<const double *>(base + off_sxr);
+    const RP *srp = reinterpret_cast<const RP *>(base + off_srp);
+    const uint16_t *sidx = reinterpret_cast<const uint16_t *>(base + off_sidx);
+    const int *meta = reinterpret_cast<const int *>(base + off_meta);
+    mbar_wait(&full_bar[s], ph);
+    const int r0 = meta[0], Rraw = meta[1], cnt = meta[3];
+    const int64_t k0 = ((int64_t)(uint32_t)meta[4]) | ((int64_t)meta[5] << 32);
+    const int64_t ka = k0 & ~(int64_t)kAlignMask;
+    const int k0l = (int)(k0 - ka), k1l = k0l + cnt;
+    const int R = Rraw & 0x7fffffff;
+    const bool head = Rraw < 0;
+    for (int i0 = 0; i0 < R; i0 += G) {  // CTA-uniform trip count (full-mask shuffles)
+      const int i = i0 + gid;
+      const bool live = i < R;
+      int a = 0, e = 0;
+      if (live) {
+        const int64_t va = (int64_t)srp[i] - ka, ve = (int64_t)srp[i + 1] - ka;
+        a = (int)(va < k0l ? k0l : (va > k1l ? k1l : va));
+        e = (int)(ve < k0l ? k0l : (ve > k1l ? k1l : ve));
+      }
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      int j = a + gl;
+      for (; j + 3 * LANES < e; j += 4 * LANES) {
+        const double x0 = sx[sidx[j]], x1 = sx[sidx[j + LANES]], x2 = sx[sidx[j + 2 * LANES]], x3 = sx[sidx[j + 3 * LANES]];
+        acc0 = fma(sval[j], x0, acc0);
+        acc1 = fma(sval[j + LANES], x1, acc1);
+        acc2 = fma(sval[j + 2 * LANES], x2, acc2);
+        acc3 = fma(sval[j + 3 * LANES], x3, acc3);
+      }
+      for (; j < e; j += LANES) acc0 = fma(sval[j], sx[sidx[j]], acc0);
+      const double acc = group_sum<LANES>((acc0 + acc1) + (acc2 + acc3));
+      if (live && gl == 0) {
+        if (i == 0 && head) carry[tile] = acc;
+        else y[r0 + i] = acc;
+        if (DOT) dsum = fma(acc, sxr[i], dsum);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  if (DOT) {
+    // block reduction over the consumer warps only (named barrier 1)
+    double v = warp_sum(dsum);
+    if (lane == 0) red[warp] = v;
+    named_bar_sync(1, kConsWarps * 32);
+    if (warp == 0) {
+      double t = lane < kConsWarps ? red[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) dot_partials[blockIdx.x] = t;
+    }
   }
 }
 
@@ -325,7 +773,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   PCGB_CHECK_LAUNCH();
   PCGB_CUDA(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   PCGB_CUDA(cudaStreamSynchronize(st));
-  P.cap_nnz = (h_stats[1] + 8 + 3) & ~3;
+  P.cap_nnz = (h_stats[1] + 16 + 7) & ~7;
   P.cap_rows = (h_stats[2] + 2 + 1) & ~1;
   P.smem_bytes = P.cap_nnz * 12 + P.cap_rows * 8 + (P.cap_rows + 2) * 4;
   P.smem_bytes = (P.smem_bytes + 127) & ~127;
@@ -358,6 +806,80 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
       PCGB_CUDA(cudaMemcpy(P.fix_cnt, fcnt.data(), P.nfix * sizeof(int), cudaMemcpyHostToDevice));
     }
   }
+  // ---- staged-x plan (k_spmv_staged): windows of x per tile + 16-bit local indices
+  P.staged = false;
+  if (P.use_tma && P.nnz > 0 && env_int("PCGB_SPMV_STAGE", 1) != 0) {
+    const int gap = env_int("PCGB_SPMV_GAP", 8);
+    const int plan_smem = (P.cap_nnz + 3 * kMaxRuns + 2 * kMaxWin + 8) * (int)sizeof(int);
+    int *d_fail = nullptr, *d_nw = nullptr;
+    PCGB_CUDA(cudaMalloc(&d_fail, sizeof(int)));
+    PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+    PCGB_CUDA(cudaMalloc(&d_nw, (size_t)P.ntiles * sizeof(int)));
+    PCGB_CUDA(cudaMalloc(&P.tile_xlen, (size_t)P.ntiles * sizeof(int)));
+    PCGB_CUDA(cudaFuncSetAttribute(k_plan_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, plan_smem));
+    k_plan_windows<<<P.ntiles, 256, plan_smem, st>>>(P.col, P.tile_k, P.cap_nnz, gap, 1, nullptr, nullptr, nullptr, nullptr, d_nw,
+                                                     P.tile_xlen, d_fail);
+    PCGB_CHECK_LAUNCH();
+    std::vector<int> h_nw((size_t)P.ntiles), h_xl((size_t)P.ntiles);
+    int h_fail = 0;
+    PCGB_CUDA(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCGB_CUDA(cudaMemcpyAsync(h_nw.data(), d_nw, (size_t)P.ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCGB_CUDA(cudaMemcpyAsync(h_xl.data(), P.tile_xlen, (size_t)P.ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCGB_CUDA(cudaStreamSynchronize(st));
+    if (!h_fail) {
+      std::vector<int> h_tw((size_t)P.ntiles + 1);
+      int64_t tot = 0;
+      int mx = 0, mw = 0;
+      for (int b = 0; b < P.ntiles; ++b) {
+        h_tw[(size_t)b] = (int)tot;
+        tot += h_nw[(size_t)b];
+        mx = std::max(mx, h_xl[(size_t)b]);
+        mw = std::max(mw, h_nw[(size_t)b]);
+      }
+      h_tw[(size_t)P.ntiles] = (int)tot;
+      if (tot < INT32_MAX) {
+        P.nwin = tot; P.max_nw = mw; P.cap_x = (mx + 2 + 1) & ~1;
+        PCGB_CUDA(cudaMalloc(&P.tile_win, ((size_t)P.ntiles + 1) * sizeof(int)));
+        PCGB_CUDA(cudaMalloc(&P.win_start, (size_t)std::max<int64_t>(tot, 1) * sizeof(int)));
+        PCGB_CUDA(cudaMalloc(&P.win_off, (size_t)std::max<int64_t>(tot, 1) * sizeof(int)));
+        PCGB_CUDA(cudaMalloc(&P.lidx, ((size_t)P.nnz + 16) * sizeof(uint16_t)));
+        PCGB_CUDA(cudaMemcpyAsync(P.tile_win, h_tw.data(), ((size_t)P.ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_plan_windows<<<P.ntiles, 256, plan_smem, st>>>(P.col, P.tile_k, P.cap_nnz, gap, 2, P.tile_win, P.lidx, P.win_start, P.win_off,
+                                                         nullptr, nullptr, d_fail);
+        PCGB_CHECK_LAUNCH();
+        PCGB_CUDA(cudaStreamSynchronize(st));
+        P.smem_staged = P.cap_nnz * 8 + P.cap_x * 8 + P.cap_rows * 8 + P.cap_nnz * 2 + (P.cap_rows + 2) * 4;
+        P.smem_staged = (P.smem_staged + 127) & ~127;
+        P.staged = P.smem_staged <= 200 * 1024;
+        if (P.staged && env_int("PCGB_SPMV_PERSIST", 1) != 0) {
+          // persistent pipelined kernel: descriptors + stage geometry
+          PCGB_CUDA(cudaMalloc(&P.tile_desc, (size_t)P.ntiles * sizeof(TileDesc)));
+          k_build_desc<RP><<<(P.ntiles + 255) / 256, 256, 0, st>>>(rp, P.tile_row, P.tile_k, P.tile_win, P.tile_xlen, P.ntiles, P.nrows,
+                                                                  P.tile_desc);
+          PCGB_CHECK_LAUNCH();
+          PCGB_CUDA(cudaStreamSynchronize(st));
+          P.stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + P.cap_rows * 8 + (P.cap_rows + 2) * 8 + P.cap_nnz * 2 + 32;
+          P.stage_bytes = (P.stage_bytes + 127) & ~127;
+          int stages = env_int("PCGB_SPMV_STAGES", 4);
+          if (stages < kProd) stages = kProd;
+          if (stages > 8) stages = 8;
+          stages -= stages % kProd;
+          const int ctas = env_int("PCGB_SPMV_CTAS", 2);
+          P.stages = stages;
+          P.smem_persist = stages * P.stage_bytes;
+          P.persist = P.smem_persist <= 200 * 1024 && P.dot_partials != nullptr;
+          P.grid_persist = std::min(P.ntiles, num_sms() * (ctas > 0 ? ctas : 1));
+        }
+      }
+    }
+    cudaFree(d_fail);
+    cudaFree(d_nw);
+    if (!P.staged) {
+      P.persist = false;
+      cudaFree(P.tile_xlen); cudaFree(P.tile_win); cudaFree(P.win_start); cudaFree(P.win_off); cudaFree(P.lidx);
+      P.tile_xlen = nullptr; P.tile_win = nullptr; P.win_start = nullptr; P.win_off = nullptr; P.lidx = nullptr;
+    }
+  }
   cudaFree(d_head);
   cudaFree(d_stats);
   return spmv_configure(P);
@@ -387,12 +909,68 @@ inline int launch_spmv_lanes(const CsrPlan &P, const double *x, double *y, cudaS
   }
 }
 
+template <int LANES, bool DOT, typename RP>
+inline int launch_staged_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
+  auto kern = k_spmv_staged<LANES, DOT, RP>;
+  if (P.ntiles == 0) return PCGB_OK;
+  if (skip == reinterpret_cast<const int *>(1)) {
+    PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return PCGB_OK;
+  }
+  kern<<<P.ntiles, kSpmvBlock, P.smem_staged, st>>>(static_cast<const RP *>(P.rowptr), P.lidx, P.val, x, y, P.tile_row, P.tile_k, P.tile_win,
+                                                    P.win_start, P.win_off, P.tile_xlen, P.nrows, P.nnz, P.cap_nnz, P.cap_rows, P.cap_x,
+                                                    P.carry, P.dot_partials, skip);
+  PCGB_CHECK_LAUNCH();
+  return PCGB_OK;
+}
+
+template <bool DOT, typename RP>
+inline int launch_staged_lanes(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
+  switch (P.lanes) {
+    case 4: return launch_staged_inst<4, DOT, RP>(P, x, y, st, skip);
+    case 8: return launch_staged_inst<8, DOT, RP>(P, x, y, st, skip);
+    case 32: return launch_staged_inst<32, DOT, RP>(P, x, y, st, skip);
+    default: return launch_staged_inst<16, DOT, RP>(P, x, y, st, skip);
+  }
+}
+
+template <int LANES, bool DOT, typename RP>
+inline int launch_persist_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
+  auto kern = k_spmv_persist<LANES, DOT, RP>;
+  if (P.ntiles == 0) return PCGB_OK;
+  if (skip == reinterpret_cast<const int *>(1)) {
+    PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return PCGB_OK;
+  }
+  kern<<<P.grid_persist, kPersistThreads, P.smem_persist, st>>>(static_cast<const RP *>(P.rowptr), P.lidx, P.val, x, y, P.tile_desc,
+                                                                 P.win_start, P.win_off, P.ntiles, P.nnz, P.cap_nnz, P.cap_rows, P.cap_x,
+                                                                 P.stages, P.stage_bytes, P.carry, P.dot_partials, skip);
+  PCGB_CHECK_LAUNCH();
+  return PCGB_OK;
+}
+
+template <bool DOT, typename RP>
+inline int launch_persist_lanes(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
+  switch (P.lanes) {
+    case 4: return launch_persist_inst<4, DOT, RP>(P, x, y, st, skip);
+    case 8: return launch_persist_inst<8, DOT, RP>(P, x, y, st, skip);
+    case 32: return launch_persist_inst<32, DOT, RP>(P, x, y, st, skip);
+    default: return launch_persist_inst<16, DOT, RP>(P, x, y, st, skip);
+  }
+}
+
 // y = A x ; with_dot additionally leaves per-tile partials of x.y in P.dot_partials.
 // Returns the number of kernel launches through *launches.
 inline int spmv_launch(const CsrPlan &P, const double *x, double *y, bool with_dot, cudaStream_t st, int *launches = nullptr,
                        const int *skip = nullptr) {
   int rc;
-  if (P.rp64) {
+  if (P.persist) {
+    if (P.rp64) rc = with_dot ? launch_persist_lanes<true, int64_t>(P, x, y, st, skip) : launch_persist_lanes<false, int64_t>(P, x, y, st, skip);
+    else rc = with_dot ? launch_persist_lanes<true, int32_t>(P, x, y, st, skip) : launch_persist_lanes<false, int32_t>(P, x, y, st, skip);
+  } else if (P.staged) {
+    if (P.rp64) rc = with_dot ? launch_staged_lanes<true, int64_t>(P, x, y, st, skip) : launch_staged_lanes<false, int64_t>(P, x, y, st, skip);
+    else rc = with_dot ? launch_staged_lanes<true, int32_t>(P, x, y, st, skip) : launch_staged_lanes<false, int32_t>(P, x, y, st, skip);
+  } else if (P.rp64) {
     if (P.use_tma) rc = with_dot ? launch_spmv_lanes<true, true, int64_t>(P, x, y, st, skip) : launch_spmv_lanes<true, false, int64_t>(P, x, y, st, skip);
     else rc = with_dot ? launch_spmv_lanes<false, true, int64_t>(P, x, y, st, skip) : launch_spmv_lanes<false, false, int64_t>(P, x, y, st, skip);
   } else {
@@ -423,6 +1001,8 @@ inline int spmv_configure(const CsrPlan &P) {
 inline void free_plan(CsrPlan &P) {
   cudaFree(P.tile_row); cudaFree(P.tile_k); cudaFree(P.carry); cudaFree(P.dot_partials);
   cudaFree(P.fix_row); cudaFree(P.fix_first); cudaFree(P.fix_cnt);
+  cudaFree(P.tile_xlen); cudaFree(P.tile_win); cudaFree(P.win_start); cudaFree(P.win_off); cudaFree(P.lidx);
+  cudaFree(P.tile_desc);
 }
 
 }  // namespace pcgb

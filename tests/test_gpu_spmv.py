@@ -38,14 +38,55 @@ def test_spmv_hex_box(cuda):
 
 
 @pytest.mark.parametrize("lanes", [4, 8, 16, 32])
-@pytest.mark.parametrize("tma", [0, 1])
-def test_spmv_variants(cuda, monkeypatch, lanes, tma):
+@pytest.mark.parametrize("variant", ["ldg", "tma", "staged", "persist"])
+def test_spmv_variants(cuda, monkeypatch, lanes, variant):
+    """The three kernels (plain loads / TMA-staged val+col with L1 gather / TMA + x staged in shared memory
+    with 16-bit local indices) and every lanes-per-row instantiation agree with scipy."""
     monkeypatch.setenv("PCGB_SPMV_LANES", str(lanes))
-    monkeypatch.setenv("PCGB_SPMV_TMA", str(tma))
+    monkeypatch.setenv("PCGB_SPMV_TMA", "0" if variant == "ldg" else "1")
+    monkeypatch.setenv("PCGB_SPMV_STAGE", "1" if variant in ("staged", "persist") else "0")
+    monkeypatch.setenv("PCGB_SPMV_PERSIST", "1" if variant == "persist" else "0")
     A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
     M = _check_spmv(A, cuda, seed=lanes)
     info = M.plan_info()
-    assert info["lanes"] == lanes and info["tma"] == tma
+    assert info["lanes"] == lanes and info["tma"] == (variant != "ldg")
+    assert info["staged"] == {"ldg": 0, "tma": 0, "staged": 1, "persist": 2}[variant]
+    if variant in ("staged", "persist"):
+        assert M.stream_bytes() < M.spmv_bytes()  # 10 B/nnz instead of 12
+
+
+@pytest.mark.parametrize("tile", [256, 512, 2048])
+@pytest.mark.parametrize("gap", [0, 8, 64])
+def test_spmv_staged_tiles_and_gaps(cuda, monkeypatch, tile, gap):
+    monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
+    monkeypatch.setenv("PCGB_SPMV_GAP", str(gap))
+    for A in (R.poisson27(11), R.hex_box_csr((7, 6, 5), (2, 0, 0), (5, 6, 5))):
+        M = _check_spmv(A, cuda, seed=tile + gap)
+        assert M.plan_info()["staged"] == 2  # persistent pipelined kernel
+
+
+@pytest.mark.parametrize("stages,ctas", [(4, 1), (4, 2), (8, 1)])
+def test_spmv_persist_pipeline_shapes(cuda, monkeypatch, stages, ctas):
+    """Ring depth / CTAs per SM of the persistent kernel; many more tiles than CTAs so every stage wraps."""
+    monkeypatch.setenv("PCGB_SPMV_STAGES", str(stages))
+    monkeypatch.setenv("PCGB_SPMV_CTAS", str(ctas))
+    monkeypatch.setenv("PCGB_SPMV_TILE", "512")
+    A = R.hex_box_csr((24, 20, 16), (0, 0, 0), (24, 20, 16))
+    M = _check_spmv(A, cuda, seed=stages)
+    info = M.plan_info()
+    assert info["staged"] == 2 and info["ntiles"] > 16 * 148 * ctas
+
+
+def test_spmv_staged_falls_back_when_not_stageable(cuda, monkeypatch):
+    """A tile whose columns are scattered over more than the shared-memory budget keeps the L1-gather kernel."""
+    n = 400000
+    rng = np.random.default_rng(12)
+    rows = np.repeat(np.arange(2000), 40)
+    cols = rng.integers(0, n, size=rows.size)
+    A = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(2000, n))
+    A.sum_duplicates()
+    M = _check_spmv(A, cuda)
+    assert M.plan_info()["staged"] == 0 and M.stream_bytes() >= M.spmv_bytes()
 
 
 @pytest.mark.parametrize("tile", [256, 1024, 4096])

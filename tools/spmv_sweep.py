@@ -11,8 +11,8 @@ base = generate_matrix(blk, device=dev)
 x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or [
-    {"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_TMA": tma}
-    for l, t, tma in itertools.product([8, 16, 32], [2048, 4096, 8192], [1, 0])]
+    {"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": sg, "PCGB_SPMV_CTAS": c}
+    for c, sg, t, l in itertools.product([2, 1], [4, 8], [1024, 2048, 3072], [8, 16])]
 for cfg in configs:
     for k, v in cfg.items():
         os.environ[k] = str(v)
@@ -28,5 +28,5 @@ for cfg in configs:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(json.dumps({**cfg, "ms": round(ms, 4), "GBps": round(M.spmv_bytes() / ms / 1e6, 1), "smem": M.plan_info()["smem_bytes"]}), flush=True)
+    print(json.dumps({**cfg, "ms": round(ms, 4), "GBps": round(M.spmv_bytes() / ms / 1e6, 1), "smem": M.plan_info()["smem_bytes"], "staged": M.plan_info()["staged"], "xcap": M.plan_info()["x_cap"], "maxw": M.plan_info()["max_windows_per_tile"]}), flush=True)
     del M
