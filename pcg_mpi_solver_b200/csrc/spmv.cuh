@@ -84,16 +84,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // try_wait suspends the warp until the phase completes or the time hint (ns) expires: no hot spinning
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)
       : "memory");
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -559,15 +560,31 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
 
   if (warp >= kConsWarps) {
     // ================= producer warp p: tiles it = p, p + kProd, ... (stage = it % stages, stages % kProd == 0)
+    // Software-pipelined: the descriptor and the window descriptors of the NEXT tile are fetched while the
+    // current one is being issued, so the only thing a stage waits for is its own TMA flight.
     const int p = warp - kConsWarps;
     const uint64_t pol = l2_evict_first_policy();
-    for (int it = p;; it += kProd) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      if (tile >= ntiles) break;
+    int it = p;
+    int tile = blockIdx.x + it * gridDim.x;
+    bool have = tile < ntiles;
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = make_int4(0, 0, 0, 0);
+    int ws = 0, wo = 0;
+    if (have) {
+      const int4 *dp = reinterpret_cast<const int4 *>(desc + tile);  // one 32-byte descriptor, broadcast load
+      d0 = __ldg(dp); d1 = __ldg(dp + 1);
+      if (lane < d1.z) { ws = __ldg(win_start + d1.y + lane); wo = __ldg(win_off + d1.y + lane); }
+    }
+    while (have) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)((it / stages) & 1);
-      const int4 *dp = reinterpret_cast<const int4 *>(desc + tile);  // one 32-byte descriptor, broadcast load
-      const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+      const int nit = it + kProd;
+      const int ntile = blockIdx.x + nit * gridDim.x;
+      const bool nhave = ntile < ntiles;
+      int4 nd0 = make_int4(0, 0, 0, 0), nd1 = make_int4(0, 0, 0, 0);
+      if (nhave) {
+        const int4 *dp = reinterpret_cast<const int4 *>(desc + ntile);
+        nd0 = __ldg(dp); nd1 = __ldg(dp + 1);
+      }
       const int64_t k0 = ((int64_t)(uint32_t)d0.x) | ((int64_t)d0.y << 32);
       const int cnt = d0.z, r0 = d0.w, Rraw = d1.x, wb = d1.y, nw = d1.z, xlen = d1.w;
       const int R = Rraw & 0x7fffffff;
@@ -580,9 +597,6 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       int *meta = reinterpret_cast<int *>(base + off_meta);
       const int64_t k1 = k0 + cnt;
       const int64_t ka = k0 & ~(int64_t)kAlignMask;
-      // window descriptors do not depend on the stage being free: fetch them while waiting
-      int ws = 0, wo = 0;
-      if (lane < nw) { ws = __ldg(win_start + wb + lane); wo = __ldg(win_off + wb + lane); }
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (lane == 0) {
         int64_t kend = (k1 + kAlignMask) & ~(int64_t)kAlignMask;
@@ -606,7 +620,6 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       }
       // raw row offsets and the x entries of the tile's own rows: asynchronous copies
       for (int i = lane; i <= R; i += 32) cp_async<sizeof(RP)>(srp + i, rowptr + r0 + i);
-      if (DOT) for (int i = lane; i < R; i += 32) cp_async<8>(sxr + i, x + r0 + i);
       // x windows (descriptor w broadcast from the lane that fetched it)
       for (int w0 = 0; w0 < nw; w0 += 32) {
         if (w0 > 0) {
@@ -622,9 +635,13 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
           for (int t = lane; t < len; t += 32) cp_async<8>(sx + o0 + t, x + s0 + t);
         }
       }
+      // window descriptors of the next tile (its descriptor was requested at the top of this iteration)
+      int nws = 0, nwo = 0;
+      if (nhave && lane < nd1.z) { nws = __ldg(win_start + nd1.y + lane); nwo = __ldg(win_off + nd1.y + lane); }
       cp_async_arrive_noinc(&full_bar[s]);       // fires when this lane's cp.async copies have landed
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);  // release: meta / tail stores of the warp
+      d0 = nd0; d1 = nd1; ws = nws; wo = nwo; it = nit; tile = ntile; have = nhave;
     }
     return;
   }
@@ -656,6 +673,8 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       const int i = i0 + gid;
       const bool live = i < R;
       int a = 0, e = 0;
+      double xr = 0.0;
+      if (DOT && live && gl == 0) xr = __ldg(x + r0 + i);  // consumed after the row loop: latency hidden
       if (live) {
         const int64_t va = (int64_t)srp[i] - ka, ve = (int64_t)srp[i + 1] - ka;
         a = (int)(va < k0l ? k0l : (va > k1l ? k1l : va));
@@ -675,7 +694,7 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       if (live && gl == 0) {
         if (i == 0 && head) carry[tile] = acc;
         else y[r0 + i] = acc;
-        if (DOT) dsum = fma(acc, sxr[i], dsum);
+        if (DOT) dsum = fma(acc, xr, dsum);
       }
     }
     __syncwarp();
@@ -742,12 +761,24 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   PCGB_CUDA(cudaStreamSynchronize(st));
   P.max_row = h_stats[0];
 
-  P.tile_items = env_int("PCGB_SPMV_TILE", 2048);  // 8 CTAs/SM: sweep in profiles/spmv_sweep_r1.txt
-  if (P.tile_items < 256) P.tile_items = 256;
   const double avg = P.nrows ? (double)P.nnz / (double)P.nrows : 0.0;
-  int lanes = avg <= 12.0 ? 4 : avg <= 100.0 ? 8 : avg <= 200.0 ? 16 : 32;
+  int lanes = avg <= 12.0 ? 4 : avg <= 85.0 ? 8 : avg <= 170.0 ? 16 : 32;
   lanes = env_int("PCGB_SPMV_LANES", lanes);
   if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) lanes = 16;
+  // Tile size: the consumers walk the rows of a tile in passes of G = 256 / lanes rows; a tile should
+  // fill ~90 % of a whole number of passes and four stages of two CTAs must fit in shared memory
+  // (sweeps: profiles/spmv_sweep_r1*.txt - 2304 items is the optimum for the 81-per-row hex matrix).
+  {
+    const double per_pass = (256.0 / lanes) * (avg + 1.0);
+    int npass = (int)(2048.0 / per_pass + 0.5);
+    if (npass < 1) npass = 1;
+    int t = (int)(0.9 * npass * per_pass);
+    t = (t + 127) & ~127;
+    if (t < 512) t = 512;
+    if (t > 2304) t = 2304;
+    P.tile_items = env_int("PCGB_SPMV_TILE", t);
+  }
+  if (P.tile_items < 256) P.tile_items = 256;
   P.lanes = lanes;
   P.snap = P.max_row <= P.tile_items / 4 && env_int("PCGB_SPMV_SNAP", 1) != 0;
   P.use_tma = env_int("PCGB_SPMV_TMA", 1) != 0;
@@ -868,7 +899,10 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           P.stages = stages;
           P.smem_persist = stages * P.stage_bytes;
           P.persist = P.smem_persist <= 200 * 1024 && P.dot_partials != nullptr;
-          P.grid_persist = std::min(P.ntiles, num_sms() * (ctas > 0 ? ctas : 1));
+          // resident CTAs per SM that really fit (227 KB of shared memory per SM, ~1 KB static per CTA)
+          int fit = (227 * 1024) / (P.smem_persist + 2048);
+          if (fit < 1) fit = 1;
+          P.grid_persist = std::min(P.ntiles, num_sms() * std::min(ctas > 0 ? ctas : 1, fit));
         }
       }
     }

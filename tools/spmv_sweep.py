@@ -12,7 +12,11 @@ x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or [
     {"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": sg, "PCGB_SPMV_CTAS": c}
-    for c, sg, t, l in itertools.product([2, 1], [4, 8], [1024, 2048, 3072], [8, 16])]
+    for c, sg, t, l in itertools.product([2], [4], [1792, 2048, 2176, 2304, 2432], [8, 16])] + [
+    {"PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2048, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 1},
+    {"PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 4096, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 1},
+    {"PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 1280, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3},
+    {"PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 1024, "PCGB_SPMV_STAGES": 8, "PCGB_SPMV_CTAS": 2}]
 for cfg in configs:
     for k, v in cfg.items():
         os.environ[k] = str(v)
