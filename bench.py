@@ -122,6 +122,7 @@ def _cpu_rank(rank, nparts, ng, pgrid, iters, conn):
     conn.send("ready")
     conn.recv()
     nglob = 3 * (ng[0]) * (ng[1] + 1) * (ng[2] + 1)
+    R.ref_pcg([part], minv, 1e-300, 2, nglob=nglob)          # untimed warm-up (page faults, BLAS init)
     t0 = time.perf_counter()
     R.ref_pcg([part], minv, 1e-300, 1, nglob=nglob)
     t1 = time.perf_counter()
@@ -171,13 +172,16 @@ def cpu_reference(ng, iters, max_procs=None):
 
 # --------------------------------------------------------------------------------------- main
 def main():
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(int(os.environ.get("PCGB_BENCH_WATCHDOG", "240")), exit=False)  # stacks on stderr if a phase hangs
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block", type=int, default=int(os.environ.get("PCGB_BENCH_BLOCK", "128")), help="hex elements per axis per GPU")
-    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -185,6 +189,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, max(args.warmup, 3)
+    CE = 50 if world == 1 else 25   # iterations per CUDA graph / host poll
 
     from pcg_mpi_solver_b200.hexmesh import block_grid
     pgrid = block_grid(max(world, 1))
@@ -197,7 +202,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        iters = max(1, min(args.steps, args.cpu_iters))
+        iters = max(3, min(args.steps, args.cpu_iters))
         for _ in range(0):
             pass
         base = cpu_reference(ng if world == 1 else tuple(args.block * g for g in pgrid), iters)
@@ -207,6 +212,12 @@ def main():
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
+
+    t_start = time.time()
+
+    def log(msg):
+        if rank == 0:
+            print(f"[bench +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
     import torch
     import torch.distributed as dist
@@ -223,6 +234,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         comm = Communicator.from_torch_distributed(dev)
 
+    log(f"process group / communicator up (world {world})")
     blocks = partition_blocks(ng, pgrid)
     blk = blocks[rank]
     blk.h = 1.0 / ng[0]
@@ -235,6 +247,7 @@ def main():
     b = load_vector(blk, device=dev)
     minv = op.jacobi()
     n = A.shape[0]
+    log(f"operator ready: n={n} nnz={A.nnz} plan={A.plan_info()['staged']} halo={op.halo_bytes()} B")
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,18 +263,20 @@ def main():
         return float(t.item())
 
     # ---- warm-up (also builds the CUDA graph of the iteration batch)
-    op.solve(b, minv, 0.0, W, fixed_iters=True, check_every=min(W, 50))
-    op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50)
+    op.solve(b, minv, 0.0, W, fixed_iters=True, check_every=min(W, CE))
+    op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=CE)
     barrier()
+    log("warm-up done")
 
     # ---- timed region: exactly K iterations, device-timed loop
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     barrier()
-    x, info = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50)
+    x, info = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=CE)
     barrier()
     loop_ms = max_over_ranks(info.loop_ms)
+    log(f"timed loop: {loop_ms / K:.4f} ms/iter")
     assert info.loop_iters == K, (info.loop_iters, K)
 
     # ---- e2e: public API, host buffers (pinned b in, x out), everything inside the timed region
@@ -272,16 +287,17 @@ def main():
     barrier()
     e0.record()
     b_dev = b_pin.to(dev, non_blocking=True)                                                   # H2D: this solve's right-hand side
-    x_e2e, info_e = op.solve(b_dev, minv, 0.0, K, fixed_iters=True, check_every=50)            # public operator API
+    x_e2e, info_e = op.solve(b_dev, minv, 0.0, K, fixed_iters=True, check_every=CE)            # public operator API
     x_host.copy_(x_e2e, non_blocking=True)                                                     # D2H: the solution
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+    log(f"e2e: {e2e_ms:.1f} ms")
     barrier()
 
     # ---- roofline pass: same K iterations with an event pair around every SpMV launch
-    _, info_k = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=50, time_kernels=True)
+    _, info_k = op.solve(b, minv, 0.0, K, fixed_iters=True, check_every=CE, time_kernels=True)
     spmv_ms = info_k.spmv_ms / max(info_k.spmv_timed, 1)
     spmv_ms = max_over_ranks(spmv_ms)
     spmv_share = info_k.spmv_ms / info_k.loop_ms if info_k.loop_ms > 0 else None
@@ -290,6 +306,7 @@ def main():
     achieved = bytes_spmv / (spmv_ms * 1e-3) / 1e9
     iter_bytes = bytes_spmv + 96 * n
     barrier()
+    log(f"roofline pass: spmv {spmv_ms:.4f} ms")
 
     if rank == 0:
         value = K / (loop_ms * 1e-3)
