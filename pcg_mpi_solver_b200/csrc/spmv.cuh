@@ -670,10 +670,7 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
     const int R = Rraw & 0x7fffffff;
     const bool head = Rraw < 0;
     for (int i0 = 0; i0 < R; i0 += G) {  // CTA-uniform trip count (full-mask shuffles)
-      // Row of this group.  With 8 lanes per row the two groups of a half-warp take rows 8 apart instead of
-      // adjacent ones: for the 81-entry rows of the hex matrix their sval / sx segments then start 8 doubles
-      // apart modulo the 16 double-wide banks - conflict-free (adjacent rows overlap in 7 of 8 banks).
-      const int i = i0 + (LANES == 8 ? ((gid >> 2) + 8 * (gid & 3)) : gid);
+      const int i = i0 + gid;  // (rows 8 apart per half-warp pair was tried: fewer bank conflicts, but slower - loses the x broadcast)
       const bool live = i < R;
       int a = 0, e = 0;
       double xr = 0.0;
