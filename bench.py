@@ -29,6 +29,8 @@ import os
 # the CPU arm forks one process per mesh part, so the same must hold here
 for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import subprocess
 import sys
 import threading
