@@ -2,7 +2,6 @@
 // sm_100a only.  No CPU fallback: every compute entry point requires a CUDA device.
 #include <cmath>
 #include <cstring>
-#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -524,11 +523,9 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
 
   int batch = opt->check_every > 0 ? opt->check_every : 16;
   if (batch > opt->maxiter) batch = opt->maxiter;
-  const bool multi = s->comm && s->comm->nranks > 1;
   const bool want_graph = opt->use_graph != 0 && !opt->time_kernels;
   size_t kpairs = 0;
   PCGB_CUDA(cudaEventRecord(s->ev_l0, st));
-  int per_iter = 0;
   int flag = 1;
   int too_small = 0;
 
@@ -552,7 +549,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
       }
       PCGB_CUDA(cudaGraphLaunch(s->gexec, st));
       graph_launch_kernels += (int64_t)s->launches_per_iter * batch;
-      per_iter = s->launches_per_iter;
     } else {
       for (int k = 0; k < batch; ++k) {
         int nl = 0;
@@ -563,7 +559,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
         }
         PCGB_TRY(enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl, ka, kb));
         s->launches += nl;
-        per_iter = nl;
       }
     }
     PCGB_TRY(fetch_ctrl(s, st));
@@ -598,7 +593,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
     flag = c.flag;  // ST_BREAK (2,3,4) or ST_EXHAUSTED (1)
     break;
   }
-  (void)multi;
   PCGB_CUDA(cudaEventRecord(s->ev_l1, st));
   PCGB_CUDA(cudaEventSynchronize(s->ev_l1));
   {
@@ -636,7 +630,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   // matvecs inside the loop = iterations started
   res->matvecs = matvecs + (int64_t)(c.iter + 1);
   res->launches = s->launches + graph_launch_kernels;
-  (void)per_iter;
   return PCGB_OK;
 }
 

@@ -554,7 +554,7 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
   }
   __syncthreads();
 
-  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | sxr[cap_rows] f64 | srp[cap_rows+2] i64 | sidx[cap_nnz] u16 | meta[8] i32
+  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | (cap_rows f64, unused) | srp[cap_rows+2] i64 | sidx[cap_nnz] u16 | meta[8] i32
   const size_t off_sx = (size_t)cap_nnz * 8, off_sxr = off_sx + (size_t)cap_x * 8, off_srp = off_sxr + (size_t)cap_rows * 8;
   const size_t off_sidx = off_srp + (size_t)(cap_rows + 2) * 8, off_meta = off_sidx + (size_t)cap_nnz * 2;
 
@@ -591,7 +591,6 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       unsigned char *base = smem_raw + (size_t)s * stage_bytes;
       double *sval = reinterpret_cast<double *>(base);
       double *sx = reinterpret_cast<double *>(base + off_sx);
-      double *sxr = reinterpret_cast<double *>(base + off_sxr);
       RP *srp = reinterpret_cast<RP *>(base + off_srp);
       uint16_t *sidx = reinterpret_cast<uint16_t *>(base + off_sidx);
       int *meta = reinterpret_cast<int *>(base + off_meta);
@@ -658,7 +657,6 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
     const unsigned char *base = smem_raw + (size_t)s * stage_bytes;
     const double *sval = reinterpret_cast<const double *>(base);
     const double *sx = reinterpret_cast<const double *>(base + off_sx);
-    const double *sxr = reinterpret_cast<const double *>(base + off_sxr);
     const RP *srp = reinterpret_cast<const RP *>(base + off_srp);
     const uint16_t *sidx = reinterpret_cast<const uint16_t *>(base + off_sidx);
     const int *meta = reinterpret_cast<const int *>(base + off_meta);

@@ -21,7 +21,7 @@ All arithmetic runs in libpcgb200.so (CUDA, sm_100a); torch only owns the device
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch
