@@ -31,6 +31,7 @@ typedef struct pcgb_csr_s *pcgb_csr_t;     /* device CSR matrix + merge-path SpM
 typedef struct pcgb_comm_s *pcgb_comm_t;   /* NCCL communicator (one rank = one GPU)            */
 typedef struct pcgb_halo_s *pcgb_halo_t;   /* interface ("halo") exchange-add plan              */
 typedef struct pcgb_solver_s *pcgb_solver_t; /* PCG workspace bound to one operator             */
+typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-by-element operator */
 
 /* error codes */
 #define PCGB_OK 0
@@ -148,6 +149,26 @@ int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const d
                const pcgb_options *opt, double *d_resvec, pcgb_result *res, void *stream);
 /* y = A x followed by the interface sum: calcMPFint (pcg_solver.py:339-342) on Eff dofs */
 int pcgb_apply(pcgb_solver_t s, const double *d_x, double *d_y, void *stream);
+
+/* ---------------------------------------------------------------- EXPERIMENTAL: matrix-free EBE operator (f1)
+ * The reference's own operator form: calcMatVecProd(...,'Strain'), pcg_solver.py:263-300, on the GPU, one
+ * pattern group per reference type group (partition_mesh.py:470-491).  Written at the end of round 1 and NOT
+ * yet exercised on hardware; nothing selects it by default.  d_idx is [nd][ne] int32 in the FREE-dof numbering
+ * (-1 = clamped dof), d_sign [nd][ne] uint8 or NULL, d_ck [ne], ke_host the nd x nd pattern matrix (host).  */
+typedef struct pcgb_ebe_group {
+  int32_t nd;
+  int64_t ne;
+  const int32_t *d_idx;
+  const unsigned char *d_sign;
+  const double *d_ck;
+  const double *ke_host;
+} pcgb_ebe_group;
+int pcgb_ebe_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, pcgb_ebe_t *out);
+int pcgb_ebe_destroy(pcgb_ebe_t E);
+int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream); /* y = K_i x (no interface sum) */
+int64_t pcgb_ebe_bytes(pcgb_ebe_t E);                                            /* algorithmic bytes per application */
+int pcgb_solver_create_ebe(pcgb_ebe_t E, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,
+                           pcgb_solver_t *out);
 
 /* ---------------------------------------------------------------- structured hex generator
  * On-device generator of the sub-assembled stiffness matrix of one box of trilinear hex

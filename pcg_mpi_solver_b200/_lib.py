@@ -33,6 +33,10 @@ class Result(ctypes.Structure):
                 ("spmv_timed", c_int64), ("loop_iters", c_int64)]
 
 
+class EbeGroup(ctypes.Structure):
+    _fields_ = [("nd", c_int32), ("ne", c_int64), ("d_idx", c_void_p), ("d_sign", c_void_p), ("d_ck", c_void_p), ("ke_host", c_void_p)]
+
+
 class HexBox(ctypes.Structure):
     _fields_ = [("ng", c_int32 * 3), ("e0", c_int32 * 3), ("ne", c_int32 * 3)]
 
@@ -65,6 +69,11 @@ SIGNATURES = {
     "pcgb_solver_destroy": (c_int, [c_void_p]),
     "pcgb_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(Options), c_void_p, POINTER(Result), c_void_p]),
     "pcgb_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcgb_ebe_create": (c_int, [c_int64, c_int, POINTER(EbeGroup), POINTER(c_void_p)]),
+    "pcgb_ebe_destroy": (c_int, [c_void_p]),
+    "pcgb_ebe_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcgb_ebe_bytes": (c_int64, [c_void_p]),
+    "pcgb_solver_create_ebe": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "pcgb_hex_nrows": (c_int64, [POINTER(HexBox)]),
     "pcgb_hex_count": (c_int, [POINTER(HexBox), c_void_p, c_void_p]),
     "pcgb_hex_fill": (c_int, [POINTER(HexBox), POINTER(c_double), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),

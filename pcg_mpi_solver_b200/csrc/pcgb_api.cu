@@ -9,11 +9,16 @@
 #include "pcg_kernels.cuh"
 #include "comm.cuh"
 #include "hexgen.cuh"
+#include "ebe.cuh"
 
 using namespace pcgb;
 
 struct pcgb_csr_s {
   CsrPlan P;
+};
+
+struct pcgb_ebe_s {
+  EbePlan P;
 };
 
 struct GraphKey {
@@ -26,6 +31,7 @@ struct GraphKey {
 
 struct pcgb_solver_s {
   pcgb_csr_t A = nullptr;
+  pcgb_ebe_t E = nullptr;       // experimental matrix-free operator (exactly one of A / E is set)
   pcgb_halo_t halo = nullptr;
   pcgb_comm_t comm = nullptr;
   int64_t n = 0;
@@ -277,14 +283,75 @@ int pcgb_halo_exchange_add(pcgb_halo_t h, double *d_y, void *stream) {
 
 int64_t pcgb_halo_bytes(pcgb_halo_t h) { return h ? h->m * 8 : 0; }
 
+// ------------------------------------------------------------------------------------ EBE operator (experimental)
+int pcgb_ebe_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, pcgb_ebe_t *out) {
+  if (!out || n < 0 || ngroups < 0 || (ngroups > 0 && !groups)) return fail(PCGB_ERR_ARG, "pcgb_ebe_create: bad argument");
+  if (n >= (1 << 30)) return fail(PCGB_ERR_ARG, "pcgb_ebe_create: more than 2^30 dofs");
+  PCGB_TRY(require_device());
+  pcgb_ebe_t E = new pcgb_ebe_s();
+  EbePlan &P = E->P;
+  P.n = n;
+  int slots = 0;
+  std::vector<int> blk_group;
+  std::vector<int64_t> blk_e0;
+  P.bytes = 16 * n;
+  for (int g = 0; g < ngroups; ++g) {
+    const pcgb_ebe_group &src = groups[g];
+    if (src.nd <= 0 || src.nd > 96 || src.ne < 0 || !src.ke_host || (src.ne > 0 && (!src.d_idx || !src.d_ck))) {
+      delete E;
+      return fail(PCGB_ERR_ARG, "pcgb_ebe_create: group %d: pattern size must be 1..96 and arrays non-null", g);
+    }
+    EbeGroup eg;
+    eg.nd = src.nd; eg.ne = src.ne; eg.idx = src.d_idx; eg.sign = src.d_sign; eg.ck = src.d_ck;
+    double *dke = nullptr;
+    PCGB_CUDA(cudaMalloc(&dke, (size_t)src.nd * src.nd * sizeof(double)));
+    PCGB_CUDA(cudaMemcpy(dke, src.ke_host, (size_t)src.nd * src.nd * sizeof(double), cudaMemcpyHostToDevice));
+    eg.ke = dke;
+    if (src.nd == 24 && slots < kEbeMaxSlots) {
+      PCGB_CUDA(cudaMemcpyToSymbol(c_ebe_ke24, src.ke_host, 576 * sizeof(double), (size_t)slots * 576 * sizeof(double)));
+      eg.slot = slots++;
+    } else {
+      for (int64_t e0 = 0; e0 < src.ne; e0 += kEbeWarpsPerBlock) { blk_group.push_back((int)P.groups.size()); blk_e0.push_back(e0); }
+    }
+    P.bytes += src.ne * ((int64_t)src.nd * (4 + (src.d_sign ? 1 : 0)) + 8);
+    P.groups.push_back(eg);
+  }
+  if (!P.groups.empty()) {
+    PCGB_CUDA(cudaMalloc(&P.d_groups, P.groups.size() * sizeof(EbeGroup)));
+    PCGB_CUDA(cudaMemcpy(P.d_groups, P.groups.data(), P.groups.size() * sizeof(EbeGroup), cudaMemcpyHostToDevice));
+  }
+  P.nblk_warp = (int)blk_group.size();
+  if (P.nblk_warp > 0) {
+    PCGB_CUDA(cudaMalloc(&P.d_blk_group, blk_group.size() * sizeof(int)));
+    PCGB_CUDA(cudaMalloc(&P.d_blk_e0, blk_e0.size() * sizeof(int64_t)));
+    PCGB_CUDA(cudaMemcpy(P.d_blk_group, blk_group.data(), blk_group.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PCGB_CUDA(cudaMemcpy(P.d_blk_e0, blk_e0.data(), blk_e0.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  }
+  *out = E;
+  return PCGB_OK;
+}
+
+int pcgb_ebe_destroy(pcgb_ebe_t E) {
+  if (!E) return PCGB_OK;
+  for (EbeGroup &g : E->P.groups) cudaFree(const_cast<double *>(g.ke));
+  cudaFree(E->P.d_groups); cudaFree(E->P.d_blk_group); cudaFree(E->P.d_blk_e0);
+  delete E;
+  return PCGB_OK;
+}
+
+int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream) {
+  if (!E || !d_x || !d_y) return fail(PCGB_ERR_ARG, "pcgb_ebe_apply: null argument");
+  return ebe_apply(E->P, d_x, d_y, (cudaStream_t)stream);
+}
+
+int64_t pcgb_ebe_bytes(pcgb_ebe_t E) { return E ? E->P.bytes : 0; }
+
 // ------------------------------------------------------------------------------------ solver
-int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_solver_t *out) {
-  if (!A || !out) return fail(PCGB_ERR_ARG, "pcgb_solver_create: null argument");
-  if (A->P.nrows != A->P.ncols) return fail(PCGB_ERR_ARG, "pcgb_solver_create: operator must be square");
+static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_solver_t *out) {
   if (halo && !comm) comm = halo->comm;
   PCGB_TRY(require_device());
   pcgb_solver_t s = new pcgb_solver_s();
-  s->A = A; s->halo = halo; s->comm = comm; s->n = A->P.nrows;
+  s->A = A; s->E = E; s->halo = halo; s->comm = comm; s->n = A ? A->P.nrows : E->P.n;
   const size_t nb = (size_t)(s->n > 0 ? s->n : 1) * sizeof(double);
   PCGB_CUDA(cudaMalloc(&s->r, nb));
   PCGB_CUDA(cudaMalloc(&s->p, nb));
@@ -293,7 +360,7 @@ int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_so
   PCGB_CUDA(cudaMalloc(&s->xown, nb));
   PCGB_CUDA(cudaMemset(s->p, 0, nb));
   PCGB_CUDA(cudaMalloc(&s->partials, 5 * kMaxVecGrid * sizeof(double)));
-  s->stage_cap = (A->P.ntiles + 4095) / 4096 + 1;
+  s->stage_cap = ((A ? A->P.ntiles : 0) + 4095) / 4096 + 1;
   PCGB_CUDA(cudaMalloc(&s->stage, (size_t)s->stage_cap * sizeof(double)));
   PCGB_CUDA(cudaMalloc(&s->red, 8 * sizeof(double)));
   PCGB_CUDA(cudaMemset(s->red, 0, 8 * sizeof(double)));
@@ -307,6 +374,17 @@ int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_so
   PCGB_CUDA(cudaEventCreate(&s->ev_l1));
   *out = s;
   return PCGB_OK;
+}
+
+int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_solver_t *out) {
+  if (!A || !out) return fail(PCGB_ERR_ARG, "pcgb_solver_create: null argument");
+  if (A->P.nrows != A->P.ncols) return fail(PCGB_ERR_ARG, "pcgb_solver_create: operator must be square");
+  return solver_create_common(A, nullptr, halo, comm, out);
+}
+
+int pcgb_solver_create_ebe(pcgb_ebe_t E, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_solver_t *out) {
+  if (!E || !out) return fail(PCGB_ERR_ARG, "pcgb_solver_create_ebe: null argument");
+  return solver_create_common(nullptr, E, halo, comm, out);
 }
 
 int pcgb_solver_destroy(pcgb_solver_t s) {
@@ -332,7 +410,8 @@ namespace {
 
 // y = A x + interface sum  (calcMPFint, pcg_solver.py:339-342)
 int op_apply(pcgb_solver_t s, const double *x, double *y, cudaStream_t st) {
-  PCGB_TRY(spmv_launch(s->A->P, x, y, false, st, &s->launches));
+  if (s->E) PCGB_TRY(ebe_apply(s->E->P, x, y, st, &s->launches));
+  else PCGB_TRY(spmv_launch(s->A->P, x, y, false, st, &s->launches));
   if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, y, st, &s->launches));
   return PCGB_OK;
 }
@@ -374,29 +453,41 @@ int rz_to_device(pcgb_solver_t s, const double *minv, const double *w, cudaStrea
 // one PCG iteration enqueued on st (pcg_solver.py:438-562); every kernel no-ops once the state is frozen
 int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, double *xb0, double *resvec, cudaStream_t st, int *nl,
                       cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr) {
-  const CsrPlan &P = s->A->P;
   const int64_t n = s->n;
   const int vg = vec_grid(n);
   const bool multi = s->comm && s->comm->nranks > 1;
   k_pupdate<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, minv, s->p);
   PCGB_CHECK_LAUNCH();
   *nl += 1;
-  if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
-  PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
-  if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
-  if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
   // p.q : per-tile partials -> (stage) -> scalar.  In the multi-GPU case the partials are those of the
   // UNASSEMBLED local product, whose rank sum equals the reference's weighted dot of the assembled q
   // (p is consistent on shared dofs and K = sum of the subdomain matrices); see DESIGN.md.
-  const double *pq_src = P.dot_partials;
-  int pq_cnt = P.persist ? P.grid_persist : P.ntiles;
-  if (pq_cnt > 8192) {
-    const int sb = (pq_cnt + 4095) / 4096;
-    k_stage_reduce<<<sb, 256, 0, st>>>(P.dot_partials, pq_cnt, s->stage);
+  const double *pq_src;
+  int pq_cnt;
+  if (s->E) {  // experimental matrix-free operator: product, then a separate unweighted dot of the local product
+    if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
+    PCGB_TRY(ebe_apply(s->E->P, s->p, s->q, st, nl, &s->d_ctrl->state));
+    if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
+    k_dot_w<<<vg, kVecBlock, 0, st>>>(n, s->p, s->q, nullptr, s->partials);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
-    pq_src = s->stage; pq_cnt = sb;
+    pq_src = s->partials; pq_cnt = vg;
+  } else {
+    const CsrPlan &P = s->A->P;
+    if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
+    PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
+    if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
+    pq_src = P.dot_partials;
+    pq_cnt = P.persist ? P.grid_persist : P.ntiles;
+    if (pq_cnt > 8192) {
+      const int sb = (pq_cnt + 4095) / 4096;
+      k_stage_reduce<<<sb, 256, 0, st>>>(P.dot_partials, pq_cnt, s->stage);
+      PCGB_CHECK_LAUNCH();
+      *nl += 1;
+      pq_src = s->stage; pq_cnt = sb;
+    }
   }
+  if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
   if (!multi) {
     k_reduce<1, 1><<<1, 256, 0, st>>>(s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();

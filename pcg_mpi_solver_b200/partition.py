@@ -101,11 +101,15 @@ class SubdomainData:
                 "OvrlpLocalDofVecList": list(self.ovrlp_full), "DofWeightVector": self.weights_full, "RefLoadVector": self.F, "Ud": self.Ud,
                 "GlobData": {"GlobNDofEff": self.n_global_eff, "GlobNDof": self.n_global}}
 
-    def to_operator(self, comm=None, device="cuda"):
-        """Upload A and build the halo plan: the `A` argument of solve() for this rank."""
+    def to_operator(self, comm=None, device="cuda", kind: str = "csr"):
+        """Upload A and build the halo plan: the `A` argument of solve() for this rank.
+        kind="ebe" selects the EXPERIMENTAL matrix-free operator (ebe.py) instead of the assembled CSR matrix."""
         from .csr import CsrMatrix
         from .solver import SubdomainOperator
-        if self.A is not None:
+        if kind == "ebe":
+            from .ebe import EbeMatrix
+            M = EbeMatrix(self.groups, self.loc_dof_eff, self.ndof, device=device)
+        elif self.A is not None:
             M = CsrMatrix.from_scipy(self.A, device=device)
         else:  # assemble on the device straight from the pattern groups
             rowptr, col, val = assemble_csr_device(self, device)

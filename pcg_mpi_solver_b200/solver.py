@@ -103,7 +103,7 @@ class SubdomainOperator:
     With comm=None (one subdomain) it is just the matrix.
     """
 
-    def __init__(self, A: CsrMatrix, comm: Communicator | None = None, nbr_ranks=(), ovrlp=(), weights=None,
+    def __init__(self, A, comm: Communicator | None = None, nbr_ranks=(), ovrlp=(), weights=None,
                  n_global: int | None = None):
         self.A, self.comm = A, comm
         self.n = A.shape[0]
@@ -127,9 +127,9 @@ class SubdomainOperator:
                 _lib.check(lib.pcgb_halo_create(comm.handle, nn, ranks, ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.n,
                                                 ctypes.byref(self._halo)), "pcgb_halo_create")
-            _lib.check(lib.pcgb_solver_create(A.handle, self._halo if self._halo else None,
-                                              comm.handle if comm is not None else None, ctypes.byref(self._solver)),
-                       "pcgb_solver_create")
+            create = lib.pcgb_solver_create if isinstance(A, CsrMatrix) else lib.pcgb_solver_create_ebe  # EbeMatrix: experimental
+            _lib.check(create(A.handle, self._halo if self._halo else None,
+                              comm.handle if comm is not None else None, ctypes.byref(self._solver)), "pcgb_solver_create")
 
     # -- calcMPFint on the Eff dofs (pcg_solver.py:339-342): y = A x, then the interface sum
     def apply(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -1,0 +1,48 @@
+"""EXPERIMENTAL matrix-free EBE operator.  The kernels were written at the end of round 1 without
+GPU time left to run them; these tests only run with PCGB_EXPERIMENTAL=1 so that an unverified kernel cannot
+poison the CUDA context of the verified suite."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_pcg as R
+from oracle.hex_mdf import write_hex_mdf
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PCGB_EXPERIMENTAL") != "1", reason="unverified round-2 work (PCGB_EXPERIMENTAL=1 to run)")]
+
+
+def test_ebe_operator_matches_csr_and_oracle_hex(cuda, tmp_path):
+    import torch
+    from pcg_mpi_solver_b200.model import load_mdf
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    write_hex_mdf(str(tmp_path), (9, 7, 5))
+    sub = partition_mesh(load_mdf(str(tmp_path)), 1, assemble=True)[0]
+    op = sub.to_operator(device=cuda, kind="ebe")
+    x = np.random.default_rng(0).standard_normal(sub.n)
+    y = op.apply(torch.from_numpy(x).to(cuda)).cpu().numpy()
+    yref = sub.A @ x
+    assert np.abs(y - yref).max() <= 1e-12 * (abs(sub.A) @ np.abs(x)).max()
+    np.testing.assert_allclose(op.jacobi().cpu().numpy(), 1.0 / sub.A.diagonal(), rtol=1e-13)
+    b = torch.from_numpy(sub.b).to(cuda)
+    xs, info = op.solve(b, op.jacobi(), 1e-10, 5000)
+    ref = R.ref_pcg([R.CsrPart(sub.A, sub.b)], [1.0 / sub.A.diagonal()], 1e-10, 5000)
+    assert info.flag == ref["Flag"] == 0 and abs(info.iters - ref["Iter"]) <= 2
+
+
+def test_ebe_operator_concrete(cuda):
+    import torch
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    zp = os.path.join(root, "oracle", "_ref", "concrete.zip")
+    if not os.path.exists(zp):
+        pytest.skip("concrete.zip not staged")
+    sub = partition_mesh(zp, 1, assemble=False)[0]
+    ebe = sub.to_operator(device=cuda, kind="ebe")
+    csr = sub.to_operator(device=cuda, kind="csr")
+    x = torch.randn(sub.n, dtype=torch.float64, device=cuda)
+    ye, yc = ebe.apply(x), csr.apply(x)
+    assert float((ye - yc).abs().max() / yc.abs().max()) <= 1e-12
+    xs, info = ebe.solve(torch.from_numpy(sub.b).to(cuda), ebe.jacobi(), 1e-7, 10000)
+    assert info.flag == 0 and abs(info.iters - 1085) <= 2
