@@ -152,8 +152,8 @@ int pcgb_apply(pcgb_solver_t s, const double *d_x, double *d_y, void *stream);
 
 /* ---------------------------------------------------------------- EXPERIMENTAL: matrix-free EBE operator (f1)
  * The reference's own operator form: calcMatVecProd(...,'Strain'), pcg_solver.py:263-300, on the GPU, one
- * pattern group per reference type group (partition_mesh.py:470-491).  Written at the end of round 1 and NOT
- * yet exercised on hardware; nothing selects it by default.  d_idx is [nd][ne] int32 in the FREE-dof numbering
+ * pattern group per reference type group (partition_mesh.py:470-491).  Written at the end of round 1: parity-tested on
+ * a B200 (tests/test_gpu_ebe.py) but not yet profiled; nothing selects it by default.  d_idx is [nd][ne] int32 in the FREE-dof numbering
  * (-1 = clamped dof), d_sign [nd][ne] uint8 or NULL, d_ck [ne], ke_host the nd x nd pattern matrix (host).  */
 typedef struct pcgb_ebe_group {
   int32_t nd;

@@ -1,4 +1,4 @@
-// ebe.cuh - EXPERIMENTAL (written in round 1 without GPU time left; not yet run on a B200, opt-in only):
+// ebe.cuh - EXPERIMENTAL, opt-in (round 1: parity-green on a B200, first timing only, not yet profiled or tuned):
 // the reference's OWN operator on the GPU - the pattern-grouped, matrix-free element-by-element product
 //     y = sum_groups scatter( S . Ke . (Ck o (S . gather(x))) )            calcMatVecProd, pcg_solver.py:263-300
 // instead of the assembled CSR form.  SURVEY.md 8(f1): ~108 B per element (24 int32 dof ids + Ck + signs)
