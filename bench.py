@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--block", type=int, default=int(os.environ.get("PCGB_BENCH_BLOCK", "128")), help="hex elements per axis per GPU")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--operator", default="csr", choices=["csr", "ebe"],
+                    help="csr = assembled merge-path SpMV (the north-star path, default); ebe = opt-in matrix-free operator (f1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,14 +244,19 @@ def main():
     blk.h = 1.0 / ng[0]
     for b_ in blocks:
         b_.h = blk.h
-    A = generate_matrix(blk, device=dev)
+    if args.operator == "ebe":
+        from pcg_mpi_solver_b200.hexmesh import generate_ebe
+        A = generate_ebe(blk, device=dev)
+    else:
+        A = generate_matrix(blk, device=dev)
     nbr, lists, w = interface_lists(blocks, rank) if world > 1 else ([], [], None)
     n_global = 3 * ng[0] * (ng[1] + 1) * (ng[2] + 1)
     op = SubdomainOperator(A, comm, nbr, lists, w, n_global=n_global)
     b = load_vector(blk, device=dev)
     minv = op.jacobi()
     n = A.shape[0]
-    log(f"operator ready: n={n} nnz={A.nnz} plan={A.plan_info()['staged']} halo={op.halo_bytes()} B")
+    is_csr = args.operator == "csr"
+    log(f"operator ready ({args.operator}): n={n} halo={op.halo_bytes()} B")
 
     def barrier():
         torch.cuda.synchronize()
@@ -314,17 +321,18 @@ def main():
         value = K / (loop_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": loop_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, n_per_gpu=n, nnz_per_gpu=A.nnz, n_global=n_global, plan=A.plan_info(),
+                "config": dict(config, operator=args.operator, n_per_gpu=n, nnz_per_gpu=A.nnz if is_csr else A.nnz_equivalent, n_global=n_global,
+                               plan=A.plan_info() if is_csr else {"kernel": "k_ebe_t24", "pattern_groups": 1},
                                halo_bytes_per_exchange=op.halo_bytes()),
                 "dof_iterations_per_s": value * n_global,
                 "e2e": {"value": K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n / K, "d2h_bytes_per_step": 8 * n / K,
                         "note": "one solve() of K iterations: pinned-host b -> device, K iterations + 2 residual matvecs + host polling, x -> pinned host"},
                 "gpu_launches": int(info.launches),
                 "clocks": clocks,
-                "roofline": {"kernel": {0: "k_spmv_merge", 1: "k_spmv_staged", 2: "k_spmv_persist"}[A.plan_info()["staged"]] + " (merge-path CSR SpMV, fp64)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": bytes_spmv, "streamed_bytes_per_launch": A.stream_bytes(),
-                             "streamed_GBps": A.stream_bytes() / (spmv_ms * 1e-3) / 1e9, "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
+                "roofline": {"kernel": ({0: "k_spmv_merge", 1: "k_spmv_staged", 2: "k_spmv_persist"}[A.plan_info()["staged"]] + " (merge-path CSR SpMV, fp64)") if is_csr else "k_ebe_t24 (matrix-free EBE operator, fp64; bytes = its own 108 B/element, not the CSR figure)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic() if is_csr else None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_spmv, "streamed_bytes_per_launch": A.stream_bytes() if is_csr else bytes_spmv,
+                             "streamed_GBps": (A.stream_bytes() if is_csr else bytes_spmv) / (spmv_ms * 1e-3) / 1e9, "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
                              "spmv_share_of_step": spmv_share,
                              "iteration": {"algorithmic_bytes": iter_bytes, "achieved_GBps": iter_bytes / (loop_ms / K * 1e-3) / 1e9,
                                            "frac": iter_bytes / (loop_ms / K * 1e-3) / 1e9 / peak}},

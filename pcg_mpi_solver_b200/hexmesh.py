@@ -129,6 +129,33 @@ def generate_matrix(block: HexBlock, device="cuda") -> CsrMatrix:
     return CsrMatrix(rowptr, col, val, (n, n))
 
 
+def hex_type_group(block: HexBlock):
+    """The box as the reference would hold it: ONE pattern type group (the Q1 hexahedron, no sign flips,
+    Ck = E*h; partition_mesh.py:443-491) in the local all-dof numbering 3*node + dir (x fastest), plus LocDofEff.
+    Returns (TypeGroup, loc_dof_eff, ndof)."""
+    from .partition import TypeGroup
+    nx, ny, nz = block.ne
+    ez, ey, ex = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ex, ey, ez = ex.ravel(), ey.ravel(), ez.ravel()
+    dofs = np.empty((24, ex.size), dtype=np.int64)
+    for l in range(8):
+        node = ((ez + ((l >> 2) & 1)) * (ny + 1) + (ey + ((l >> 1) & 1))) * (nx + 1) + (ex + (l & 1))
+        for d in range(3):
+            dofs[3 * l + d] = 3 * node + d
+    lz, ly, lx = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    free_nodes = np.nonzero(lx.ravel() >= block.x_lo)[0]     # ascending -> the free numbering of generate_matrix
+    eff = (3 * free_nodes[:, None] + np.arange(3)[None, :]).ravel()
+    grp = TypeGroup(0, dofs, np.zeros(dofs.shape, dtype=bool), np.full(ex.size, block.E * block.h), hex_element_stiffness(1.0, block.nu), None)
+    return grp, eff, 3 * (nx + 1) * (ny + 1) * (nz + 1)
+
+
+def generate_ebe(block: HexBlock, device="cuda"):
+    """The same box as a matrix-free EBE operator (ebe.EbeMatrix); opt-in companion of generate_matrix."""
+    from .ebe import EbeMatrix
+    grp, eff, ndof = hex_type_group(block)
+    return EbeMatrix([grp], eff, ndof, device=device)
+
+
 def load_vector(block: HexBlock, traction: float = 1.0, device="cuda") -> torch.Tensor:
     """b = Fext[LocDofEff]: consistent nodal loads of a uniform -z traction on the global x = max face
     (assembled values, identical on every copy of a shared dof, like RefLoadVector = F[DofVector])."""

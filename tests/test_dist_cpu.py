@@ -69,3 +69,23 @@ def test_interface_lists_gloo(world, ng):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_hex_type_group_is_the_same_operator_as_the_csr_box():
+    """hexmesh.hex_type_group (input of the opt-in EBE operator) == the assembled box, through the CPU oracle."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_pcg as R
+    from pcg_mpi_solver_b200.hexmesh import HexBlock, hex_type_group
+    for e0 in ((0, 0, 0), (3, 1, 0)):
+        blk = HexBlock((9, 6, 5), e0, (4, 3, 2), h=0.25)
+        grp, eff, ndof = hex_type_group(blk)
+        assert eff.size == blk.n
+        mp_ = {"Id": 0, "NDOF": ndof, "LocDofEff": eff, "NbrMPIdVector": [], "OvrlpLocalDofVecList": [], "DofWeightVector": np.ones(ndof),
+               "SubDomainData": {"StrucDataList": [{"ElemList_LocDofVector": grp.loc_dof, "ElemList_SignVector": grp.sign, "ElemList_Ck": grp.ck,
+                                                    "ElemStiffMat": grp.ke, "ElemDiagStiffMat": np.diag(grp.ke).copy()}]},
+               "Flat_ElemLocDof": grp.loc_dof.flatten(), "NCountDof": grp.loc_dof.size}
+        part = R.EbePart(mp_)
+        A = R.hex_box_csr(blk.ng, blk.e0, blk.ne, h=blk.h)
+        x = np.random.default_rng(1).standard_normal(blk.n)
+        y = R.Operator([part]).apply([x])[0]
+        assert np.abs(y - A @ x).max() <= 1e-13 * np.abs(A @ x).max()
