@@ -2,17 +2,12 @@
 import json, sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
-from oracle.hex_parts import hex_box_part
-from pcg_mpi_solver_b200.ebe import EbeMatrix
-from pcg_mpi_solver_b200.partition import TypeGroup
+from pcg_mpi_solver_b200.hexmesh import HexBlock, generate_ebe
 from pcg_mpi_solver_b200.solver import SubdomainOperator
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda:0")
 t0 = time.time()
-mp = hex_box_part((B,) * 3, (0, 0, 0), (B,) * 3, h=1.0 / B)
-g = mp["SubDomainData"]["StrucDataList"][0]
-grp = TypeGroup(0, g["ElemList_LocDofVector"], g["ElemList_SignVector"], g["ElemList_Ck"], g["ElemStiffMat"], None)
-E = EbeMatrix([grp], mp["LocDofEff"], mp["NDOF"], device=dev)
+E = generate_ebe(HexBlock((B,) * 3, (0, 0, 0), (B,) * 3, h=1.0 / B), device=dev)
 op = SubdomainOperator(E)
 n = E.shape[0]
 x = torch.randn(n, dtype=torch.float64, device=dev); y = torch.empty_like(x)
@@ -27,6 +22,6 @@ b = torch.zeros(n, dtype=torch.float64, device=dev); b[2::3] = -1e-4
 minv = op.jacobi()
 op.solve(b, minv, 0.0, 20, fixed_iters=True, check_every=20)
 _, info = op.solve(b, minv, 0.0, 200, fixed_iters=True, check_every=50)
-print(json.dumps({"block": B, "n": n, "elements": int(g["ElemList_Ck"].size), "ebe_apply_ms": ms, "ebe_bytes": E.spmv_bytes(),
+print(json.dumps({"block": B, "n": n, "elements": B ** 3, "ebe_apply_ms": ms, "ebe_bytes": E.spmv_bytes(),
                   "ebe_GBps": E.spmv_bytes() / ms / 1e6, "pcg_ms_per_iter": info.loop_ms / 200, "pcg_it_per_s": 200 / (info.loop_ms * 1e-3),
                   "setup_s": time.time() - t0}))
