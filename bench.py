@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--block", type=int, default=int(os.environ.get("PCGB_BENCH_BLOCK", "128")), help="hex elements per axis per GPU")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="hex", choices=["hex", "hex_metis", "concrete"],
+                    help="hex = block-partitioned device-generated mesh (default, C2/C5); hex_metis = same global mesh through "
+                         "partition_mesh()/METIS (C3); concrete = data/concrete.zip through partition_mesh()/METIS (C4)")
     ap.add_argument("--operator", default="csr", choices=["csr", "ebe"],
                     help="csr = assembled merge-path SpMV (the north-star path, default); ebe = opt-in matrix-free operator (f1)")
     args = ap.parse_args()
@@ -239,20 +242,44 @@ def main():
         comm = Communicator.from_torch_distributed(dev)
 
     log(f"process group / communicator up (world {world})")
-    blocks = partition_blocks(ng, pgrid)
-    blk = blocks[rank]
-    blk.h = 1.0 / ng[0]
-    for b_ in blocks:
-        b_.h = blk.h
-    if args.operator == "ebe":
-        from pcg_mpi_solver_b200.hexmesh import generate_ebe
-        A = generate_ebe(blk, device=dev)
+    if args.workload == "hex":
+        blocks = partition_blocks(ng, pgrid)
+        blk = blocks[rank]
+        blk.h = 1.0 / ng[0]
+        for b_ in blocks:
+            b_.h = blk.h
+        if args.operator == "ebe":
+            from pcg_mpi_solver_b200.hexmesh import generate_ebe
+            A = generate_ebe(blk, device=dev)
+        else:
+            A = generate_matrix(blk, device=dev)
+        nbr, lists, w = interface_lists(blocks, rank) if world > 1 else ([], [], None)
+        n_global = 3 * ng[0] * (ng[1] + 1) * (ng[2] + 1)
+        op = SubdomainOperator(A, comm, nbr, lists, w, n_global=n_global)
+        b = load_vector(blk, device=dev)
     else:
-        A = generate_matrix(blk, device=dev)
-    nbr, lists, w = interface_lists(blocks, rank) if world > 1 else ([], [], None)
-    n_global = 3 * ng[0] * (ng[1] + 1) * (ng[2] + 1)
-    op = SubdomainOperator(A, comm, nbr, lists, w, n_global=n_global)
-    b = load_vector(blk, device=dev)
+        # the general pipeline: model -> METIS (run_metis.py) -> subdomain builder (partition_mesh.py) -> device assembly
+        from pcg_mpi_solver_b200.partition import partition_mesh
+        if args.workload == "concrete":
+            zp = os.path.join(ROOT, "oracle", "_ref", "concrete.zip")
+            if not os.path.exists(zp):
+                zp = "/root/reference/data/concrete.zip"
+            ep = None
+            gold = os.path.join(ROOT, "tests", "golden", f"concrete_elepart_{world}.npy")
+            if os.path.exists(gold):
+                ep = np.load(gold).astype(np.int64)       # the partition the reference's 8-rank golden run used
+            subs = partition_mesh(zp, world, elepart=ep, assemble=False)
+            config["workload"] = f"data/concrete.zip (124 693 octree SBFEM elements, 616 413 free dofs), METIS {world}-way, Jacobi-PCG fixed {K} iterations"
+        else:
+            from pcg_mpi_solver_b200.hexmesh import hex_mdf_model
+            subs = partition_mesh(hex_mdf_model(ng), world, assemble=False)
+            config["workload"] = config["workload"].replace("trilinear hex elastostatics", f"trilinear hex elastostatics, METIS {world}-way element partition")
+        sub = subs[rank]
+        n_global = sub.n_global_eff
+        op = sub.to_operator(comm, device=dev, kind=args.operator)
+        A = op.A
+        b = torch.from_numpy(sub.b).to(dev)
+        del subs
     minv = op.jacobi()
     n = A.shape[0]
     is_csr = args.operator == "csr"
@@ -337,7 +364,7 @@ def main():
                              "iteration": {"algorithmic_bytes": iter_bytes, "achieved_GBps": iter_bytes / (loop_ms / K * 1e-3) / 1e9,
                                            "frac": iter_bytes / (loop_ms / K * 1e-3) / 1e9 / peak}},
                 "solve_check": {"flag": info.flag, "relres_after_K": info.relres}}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "hex":
             try:
                 line["cpu_baseline"] = cpu_reference(ng, max(1, args.cpu_iters))
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number

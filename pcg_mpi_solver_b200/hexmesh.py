@@ -156,6 +156,44 @@ def generate_ebe(block: HexBlock, device="cuda"):
     return EbeMatrix([grp], eff, ndof, device=device)
 
 
+def hex_mdf_model(ng, E: float = 1.0, nu: float = 0.3, h: float | None = None, traction: float = 1.0):
+    """The structured hex problem as an in-memory `MdfModel` (the reference's model-definition schema, SURVEY
+    Appendix A) so that the general pipeline - `partition_mesh(model, nparts)` with METIS, the subdomain builder,
+    device assembly / EBE - can run on it (config C3: the 128^3 mesh partitioned 8-way by METIS).
+    Global numbering: node = (gz*(ny+1)+gy)*(nx+1)+gx, dof = 3*node+dir; one pattern type (the Q1 hexahedron)."""
+    from .model import MdfModel
+    nx, ny, nz = ng
+    h = 1.0 / nx if h is None else h
+    ne = nx * ny * nz
+    ez, ey, ex = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ex, ey, ez = ex.ravel(), ey.ravel(), ez.ravel()
+    nodes = np.empty((ne, 8), dtype=np.int64)
+    for l in range(8):
+        nodes[:, l] = ((ez + ((l >> 2) & 1)) * (ny + 1) + (ey + ((l >> 1) & 1))) * (nx + 1) + (ex + (l & 1))
+    dofs = (3 * nodes[:, :, None] + np.arange(3)[None, None, :]).reshape(ne, 24)
+
+    def offsets(per):
+        s = np.arange(ne, dtype=np.int64) * per
+        return np.stack([s, s + per - 1], axis=1)             # INCLUSIVE ends, like the reference's *Offset arrays
+
+    gz, gy, gx = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    gx, gy, gz = gx.ravel(), gy.ravel(), gz.ravel()
+    ndof = 3 * gx.size
+    F = np.zeros(ndof)
+    face = gx == nx
+    cy = np.where((gy == 0) | (gy == ny), 0.5, 1.0)
+    cz = np.where((gz == 0) | (gz == nz), 0.5, 1.0)
+    F[3 * np.nonzero(face)[0] + 2] = (-traction * h * h * cy * cz)[face]
+    fixed = np.sort((3 * np.nonzero(gx == 0)[0][:, None] + np.arange(3)[None, :]).ravel())
+    eff = np.setdiff1d(np.arange(ndof), fixed)
+    return MdfModel(name=f"hex{nx}x{ny}x{nz}", n_elem=ne, n_dof=ndof, n_dof_eff=eff.size,
+                    node_flat=nodes.ravel().astype(np.int32), node_offset=offsets(8),
+                    dof_flat=dofs.ravel().astype(np.int32), dof_offset=offsets(24),
+                    sign_flat=np.zeros(ne * 24, dtype=bool), sign_offset=offsets(24),
+                    etype=np.zeros(ne, dtype=np.int32), ck=np.full(ne, E * h), F=F, Ud=np.zeros(ndof),
+                    dof_eff=eff.astype(np.int64), fixed_dof=fixed.astype(np.int64), ke=[hex_element_stiffness(1.0, nu)], dt=0.0)
+
+
 def load_vector(block: HexBlock, traction: float = 1.0, device="cuda") -> torch.Tensor:
     """b = Fext[LocDofEff]: consistent nodal loads of a uniform -z traction on the global x = max face
     (assembled values, identical on every copy of a shared dof, like RefLoadVector = F[DofVector])."""

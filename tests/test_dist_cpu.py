@@ -89,3 +89,30 @@ def test_hex_type_group_is_the_same_operator_as_the_csr_box():
         x = np.random.default_rng(1).standard_normal(blk.n)
         y = R.Operator([part]).apply([x])[0]
         assert np.abs(y - A @ x).max() <= 1e-13 * np.abs(A @ x).max()
+
+
+def test_hex_mdf_model_equals_the_mdf_files_the_reference_consumed(tmp_path):
+    """hexmesh.hex_mdf_model (in-memory) == oracle/hex_mdf.py's files read back with load_mdf - the files the
+    unmodified reference ran on for tests/golden/hex_ref.*; and METIS + builder + assembly run on it."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_pcg as R
+    from oracle.hex_mdf import write_hex_mdf
+    from pcg_mpi_solver_b200.hexmesh import hex_mdf_model
+    from pcg_mpi_solver_b200.model import load_mdf
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    ng = (10, 8, 6)
+    write_hex_mdf(str(tmp_path), ng)
+    a, b = load_mdf(str(tmp_path)), hex_mdf_model(ng)
+    for f in ("node_flat", "node_offset", "dof_flat", "dof_offset", "sign_flat", "sign_offset", "etype", "ck", "F", "Ud", "dof_eff", "fixed_dof"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert (a.n_elem, a.n_dof, a.n_dof_eff) == (b.n_elem, b.n_dof, b.n_dof_eff)
+    assert np.abs(a.ke[0] - b.ke[0]).max() <= 1e-15        # oracle's and product's Q1 matrices (independent codes)
+    subs = partition_mesh(b, 4)                               # METIS 4-way, host assembly
+    assert sum(s.weights.sum() for s in subs) == b.n_dof_eff
+    parts = [R.CsrPart(s.A, s.b, s.nbr, s.ovrlp, s.weights, part_id=s.id) for s in subs]
+    out = R.ref_pcg(parts, R.Operator(parts).jacobi(), 1e-10, 5000, nglob=b.n_dof_eff)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hex_ref.npz"))
+    u = np.zeros(b.n_dof)
+    for s, x in zip(subs, out["X"]):
+        u[s.dof_eff_global] = x
+    assert out["Flag"] == 0 and np.linalg.norm(u - gold["U_box1"]) <= 1e-9 * np.linalg.norm(gold["U_box1"])
