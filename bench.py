@@ -199,20 +199,20 @@ def main():
     CE = 50 if world == 1 else 25   # iterations per CUDA graph / host poll
 
     from pcg_mpi_solver_b200.hexmesh import block_grid
-    pgrid = block_grid(max(world, 1))
+    # the CPU arm works on the SAME global mesh as the N-GPU arm even when it is started without torchrun
+    mesh_world = max(world, args.gpus if args.impl == "reference" else 1, 1)
+    pgrid = block_grid(mesh_world)
     ng = tuple(args.block * pgrid[a] for a in range(3))
     config = {"workload": f"hex{args.block}^3 elements per GPU, global {ng[0]}x{ng[1]}x{ng[2]} trilinear hex elastostatics "
                           f"(E=1, nu=0.3, h=1/{ng[0]}), clamped x=0, traction on x=max, Jacobi-PCG fixed {K} iterations",
-              "per_gpu_block": args.block, "process_grid": list(pgrid), "parallelism": f"dd{world}",
+              "per_gpu_block": args.block, "process_grid": list(pgrid), "parallelism": f"dd{mesh_world}",
               "l2_policy": "inputs larger than L2 (CSR 6.1 GB per GPU vs 126 MB L2), no flush needed"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         iters = max(3, min(args.steps, args.cpu_iters))
-        for _ in range(0):
-            pass
-        base = cpu_reference(ng if world == 1 else tuple(args.block * g for g in pgrid), iters)
+        base = cpu_reference(ng, iters)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
                 "warmup": 0, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
