@@ -104,42 +104,36 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU reference arm
-def _cpu_rank(rank, nparts, ng, pgrid, iters, conn):
-    """One 'MPI rank' of the oracle port: its own box, lock-step PCG via pipes is overkill for a timing
-    sample, so every rank runs the per-rank work of an iteration (EBE matvec + the vector ops) on its own
-    box and the wall time of the slowest rank is taken, like a barrier-synchronised iteration."""
-    os.environ["OMP_NUM_THREADS"] = "1"
-    try:
-        os.sched_setaffinity(0, {rank % os.cpu_count()})
-    except Exception:
-        pass
+def _cpu_rank(rank, size, comm, ng, pgrid, iters):
+    """One 'MPI rank' of the oracle port (oracle/spmd.py): its own box of the mesh as an element-by-element part,
+    reductions and the interface exchange through shared memory + barriers - the reference's communication pattern
+    (3 allreduces + 1 neighbour exchange per iteration, pcg_solver.py:303-334, 622-628)."""
     from oracle import ref_pcg as R
-    from oracle.hex_parts import hex_box_part
+    from oracle.hex_parts import hex_box_part_spmd
     from pcg_mpi_solver_b200.hexmesh import partition_blocks
-    blk = partition_blocks(ng, pgrid)[rank]
-    part = R.EbePart(hex_box_part(blk.ng, blk.e0, blk.ne, rank, h=1.0 / ng[0]))
-    R.update_bc([part])
-    op = R.Operator([part])
-    minv = op.jacobi()
-    conn.send("ready")
-    conn.recv()
+    blocks = partition_blocks(ng, pgrid)
+    part = R.EbePart(hex_box_part_spmd(blocks, rank, h=1.0 / ng[0]))
+    comm.setup_halo(part, comm._halo_box)
+    R.update_bc([part], comm=comm)
+    minv = R.Operator([part], comm).jacobi()
     nglob = 3 * (ng[0]) * (ng[1] + 1) * (ng[2] + 1)
-    R.ref_pcg([part], minv, 1e-300, 2, nglob=nglob)          # untimed warm-up (page faults, BLAS init)
+    kw = dict(nglob=nglob, comm=comm)
+    R.ref_pcg([part], minv, 1e-300, 2, **kw)                 # untimed warm-up (page faults, BLAS init)
     t0 = time.perf_counter()
-    R.ref_pcg([part], minv, 1e-300, 1, nglob=nglob)
+    R.ref_pcg([part], minv, 1e-300, 1, **kw)
     t1 = time.perf_counter()
-    out = R.ref_pcg([part], minv, 1e-300, 1 + iters, nglob=nglob)
+    out = R.ref_pcg([part], minv, 1e-300, 1 + iters, **kw)
     t2 = time.perf_counter()
     # difference of two runs = `iters` loop iterations only (set-up and the two residual matvecs cancel)
-    conn.send(((t2 - t1) - (t1 - t0), out["Iter"], part.n))
+    return ((t2 - t1) - (t1 - t0), out["Iter"], part.n)
 
 
 def cpu_reference(ng, iters, max_procs=None):
-    """iterations/s of the oracle port on this host: the mesh is cut into P slabs/boxes (P = cores, power
-    of two, <= 64), one process per part and one BLAS thread per process exactly like the reference's
-    `mpiexec -np P` with OMP_NUM_THREADS=1 (pcg_solver.py:10-15); interface exchange is omitted (it is
-    < 10 % of the reference's time, solver_demo.ipynb:380-408) which favours the CPU side."""
-    import multiprocessing as mp
+    """iterations/s of the oracle port on this host: the mesh is cut into P boxes (P = cores, power of two, <= 64),
+    one process per part and one BLAS thread per process exactly like the reference's `mpiexec -np P` with
+    OMP_NUM_THREADS=1 (pcg_solver.py:10-15); the parts are coupled like the reference's ranks (shared-memory
+    allreduce and interface exchange, oracle/spmd.py)."""
+    from oracle.spmd import run_spmd
     from pcg_mpi_solver_b200.hexmesh import block_grid
     cores = os.cpu_count() or 1
     try:
@@ -149,26 +143,14 @@ def cpu_reference(ng, iters, max_procs=None):
     p = 1
     while p * 2 <= min(cores, max_procs or 64):
         p *= 2
-    pgrid = block_grid(p)
-    ctx = mp.get_context("fork")
-    procs, conns = [], []
-    for r in range(p):
-        a, b = ctx.Pipe()
-        pr = ctx.Process(target=_cpu_rank, args=(r, p, ng, pgrid, iters, b))
-        pr.start()
-        procs.append(pr)
-        conns.append(a)
-    for c in conns:
-        c.recv()
-    for c in conns:
-        c.send("go")
-    res = [c.recv() for c in conns]
-    for pr in procs:
-        pr.join()
+    while p > 1 and any(g > n for g, n in zip(block_grid(p), ng)):
+        p //= 2
+    res = run_spmd(p, _cpu_rank, (ng, block_grid(p), iters))
     dt = max(r[0] for r in res)
     return {"value": iters / dt, "unit": UNIT, "cores": p, "kind": "port",
-            "sample": f"{iters} PCG loop iterations (difference of a {iters}+1 and a 1 iteration run) of the numpy element-by-element reference path on the same "
-                      f"{ng[0]}x{ng[1]}x{ng[2]} hex mesh cut into {p} boxes, 1 process/box, 1 BLAS thread each, no interface exchange",
+            "sample": f"{iters} PCG loop iterations (difference of a {iters}+1 and a 1 iteration run) of the numpy element-by-element reference path "
+                      f"(oracle/ref_pcg.py <- pcg_solver.py:242-598) on the same {ng[0]}x{ng[1]}x{ng[2]} hex mesh cut into {p} boxes, 1 process/box, "
+                      f"1 BLAS thread each, shared-memory allreduce + interface exchange every iteration",
             "seconds": dt}
 
 

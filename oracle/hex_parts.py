@@ -64,3 +64,27 @@ def link_parts(parts):
             if p["Id"] > q["Id"]:                                                              # :885-887
                 p["DofWeightVector"][dofs] = 0
     return parts
+
+
+def hex_box_part_spmd(blocks, rank, h, traction=1.0):
+    """One rank's part INCLUDING its neighbour tables, built without the other parts in memory: the neighbours' node
+    ids follow from their boxes (same rule as link_parts / partition_mesh.py:805-887)."""
+    b = blocks[rank]
+    p = hex_box_part(b.ng, b.e0, b.ne, rank, h=h, traction=traction)
+    ng = b.ng
+    for q_id, q in enumerate(blocks):
+        if q_id == rank:
+            continue
+        lo = [max(b.e0[a], q.e0[a]) for a in range(3)]
+        hi = [min(b.e0[a] + b.ne[a], q.e0[a] + q.ne[a]) for a in range(3)]
+        if any(lo[a] > hi[a] for a in range(3)):
+            continue
+        gz, gy, gx = np.meshgrid(np.arange(lo[2], hi[2] + 1), np.arange(lo[1], hi[1] + 1), np.arange(lo[0], hi[0] + 1), indexing="ij")
+        common = ((gz * (ng[1] + 1) + gy) * (ng[0] + 1) + gx).ravel()          # ascending global node id
+        loc = np.searchsorted(p["NodeIdVector"], common)                         # NodeIdVector is ascending for a box
+        dofs = (3 * loc + np.array([[0], [1], [2]])).T.ravel()
+        p["NbrMPIdVector"].append(q_id)
+        p["OvrlpLocalDofVecList"].append(dofs)
+        if rank > q_id:
+            p["DofWeightVector"][dofs] = 0
+    return p

@@ -122,10 +122,11 @@ def exchange_add(parts, ys):
 class Operator:
     """calcMPFint (pcg_solver.py:339-342) over all parts, on free-dof vectors."""
 
-    def __init__(self, parts):
+    def __init__(self, parts, comm=None):
         self.parts = parts
         self.ebe = isinstance(parts[0], EbePart)
         self.matvecs = 0
+        self.comm = comm   # SPMD mode (oracle/spmd.py): this process holds ONE part, neighbours live in other processes
 
     def apply(self, xs):
         self.matvecs += 1
@@ -135,23 +136,30 @@ class Operator:
                 xf = np.zeros(p.ndof)
                 xf[p.eff] = x                      # :482  (fixed dofs stay zero)
                 fulls.append(p.matvec_full(xf))
-            fulls = exchange_add_full(self.parts, fulls)
+            fulls = self.comm.exchange_add_full(self.parts[0], fulls[0]) if self.comm else exchange_add_full(self.parts, fulls)
+            fulls = [fulls] if self.comm else fulls
             return [f[p.eff] for p, f in zip(self.parts, fulls)]  # :484
         return exchange_add(self.parts, [p.matvec(x) for p, x in zip(self.parts, xs)])
 
     def jacobi(self):
         """updatePreconditioner (pcg_solver.py:346-352): 1/diag(K) assembled over the interface."""
         if self.ebe:
-            ds = exchange_add_full(self.parts, [p.diag_full() for p in self.parts])
+            if self.comm:
+                ds = [self.comm.exchange_add_full(self.parts[0], self.parts[0].diag_full())]
+            else:
+                ds = exchange_add_full(self.parts, [p.diag_full() for p in self.parts])
             return [(1.0 / d)[p.eff] for p, d in zip(self.parts, ds)]
         ds = exchange_add(self.parts, [p.diag() for p in self.parts])
         return [1.0 / d for d in ds]
 
 
-def update_bc(parts, delta=1.0):
+def update_bc(parts, delta=1.0, comm=None):
     """updateBC (pcg_solver.py:226-238) for EbeParts: Fext = F*delta - K (Ud*delta); sets p.b and returns Udi."""
     udis = [np.asarray(p.mp["Ud"], dtype=float) * delta for p in parts]
-    fdis = exchange_add_full(parts, [p.matvec_full(u) for p, u in zip(parts, udis)])
+    if comm:
+        fdis = [comm.exchange_add_full(parts[0], parts[0].matvec_full(udis[0]))]
+    else:
+        fdis = exchange_add_full(parts, [p.matvec_full(u) for p, u in zip(parts, udis)])
     for p, fdi in zip(parts, fdis):
         fext = np.asarray(p.mp["RefLoadVector"], dtype=float) * delta - fdi
         p.b = fext[p.eff]                          # :377
@@ -159,7 +167,7 @@ def update_bc(parts, delta=1.0):
 
 
 # ----------------------------------------------------------------------------------------- PCG
-def _mpi_sum(vals):
+def _mpi_sum_local(vals):
     """MPI_SUM (pcg_solver.py:622-628): allreduce(SUM) - here a sum over the parts in rank order."""
     tot = vals[0]
     for v in vals[1:]:
@@ -167,15 +175,18 @@ def _mpi_sum(vals):
     return tot
 
 
-def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True):
+def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True, comm=None):
     """PCG(RefMeshPart), pcg_solver.py:356-598, for all parts in lock-step.
 
+    comm: None = all parts live in this process (lock-step emulation); an oracle/spmd.ShmComm = SPMD mode, `parts`
+    holds this process's single part and reductions / interface sums go through shared memory.
     parts: list of CsrPart / EbePart (fields b, x0, w).  minv: list of InvDiagPreCondVector0 per part
     (ignored when exist_dp0 is False, :446-451).  nglob: GlobNDofEff.  Returns a dict with
     X (list per part), Flag, RelRes, Iter and bookkeeping.  If `resvec` is a list, ||r|| per
     iteration is appended (the reference has this commented out, :428-434, :520-525).
     """
-    op = Operator(parts)
+    op = Operator(parts, comm)
+    _mpi_sum = (lambda vals: comm.allreduce(_mpi_sum_local(vals))) if comm else _mpi_sum_local  # noqa: F811
     P = len(parts)
     rng = range(P)
     W = [p.w for p in parts]
