@@ -41,6 +41,8 @@ typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-b
 #define PCGB_ERR_NODEVICE (-4)
 
 int pcgb_version(void);
+/* sizeof(pcgb_options), sizeof(pcgb_result), sizeof(pcgb_hex_box), sizeof(pcgb_ebe_group): lets a binding verify its struct layouts */
+void pcgb_abi_sizes(int32_t out[4]);
 const char *pcgb_last_error(void); /* thread-local message of the last failing call */
 int pcgb_device_count(void);       /* number of visible CUDA devices (0 on a CPU box) */
 

@@ -44,6 +44,7 @@ class HexBox(ctypes.Structure):
 # name -> (restype, argtypes); every symbol declared in include/pcgb200.h
 SIGNATURES = {
     "pcgb_version": (c_int, []),
+    "pcgb_abi_sizes": (None, [POINTER(c_int32)]),
     "pcgb_last_error": (c_char_p, []),
     "pcgb_device_count": (c_int, []),
     "pcgb_csr_create": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),

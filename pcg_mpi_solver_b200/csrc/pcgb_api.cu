@@ -64,6 +64,10 @@ static int require_device() {
 extern "C" {
 
 int pcgb_version(void) { return PCGB_VERSION; }
+void pcgb_abi_sizes(int32_t out[4]) {
+  out[0] = (int32_t)sizeof(pcgb_options); out[1] = (int32_t)sizeof(pcgb_result);
+  out[2] = (int32_t)sizeof(pcgb_hex_box); out[3] = (int32_t)sizeof(pcgb_ebe_group);
+}
 const char *pcgb_last_error(void) { return last_error().c_str(); }
 int pcgb_device_count(void) {
   int n = 0;

@@ -29,9 +29,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from pcg_mpi_solver_b200 import _lib
-    assert ctypes.sizeof(_lib.Options) == 48
-    assert ctypes.sizeof(_lib.Result) == 88
-    assert ctypes.sizeof(_lib.HexBox) == 36
+    sizes = (ctypes.c_int32 * 4)()
+    _lib.load().pcgb_abi_sizes(sizes)                      # sizeof() as the C++ compiler sees the structs of pcgb200.h
+    assert ctypes.sizeof(_lib.Options) == sizes[0]
+    assert ctypes.sizeof(_lib.Result) == sizes[1]
+    assert ctypes.sizeof(_lib.HexBox) == sizes[2] == 36
+    assert ctypes.sizeof(_lib.EbeGroup) == sizes[3]
 
 
 def test_no_cpu_fallback():
