@@ -32,6 +32,7 @@ typedef struct pcgb_comm_s *pcgb_comm_t;   /* NCCL communicator (one rank = one 
 typedef struct pcgb_halo_s *pcgb_halo_t;   /* interface ("halo") exchange-add plan              */
 typedef struct pcgb_solver_s *pcgb_solver_t; /* PCG workspace bound to one operator             */
 typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-by-element operator */
+typedef struct pcgb_ebe2_s *pcgb_ebe2_t;   /* round-2 preparation: coloured (atomics-free, deterministic) variant */
 
 /* error codes */
 #define PCGB_OK 0
@@ -171,6 +172,14 @@ int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream); 
 int64_t pcgb_ebe_bytes(pcgb_ebe_t E);                                            /* algorithmic bytes per application */
 int pcgb_solver_create_ebe(pcgb_ebe_t E, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,
                            pcgb_solver_t *out);
+
+/* Round-2 preparation (NOT yet run on hardware, operator-level only, not reachable from pcgb_solve): the same operator
+ * with an atomics-free deterministic scatter.  groups[] = one entry per (pattern group, colour) slice, sorted by
+ * colour; phase[g] = colour of entry g; no two elements of one colour may share a dof (coloring.py).            */
+int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const int32_t *phase, pcgb_ebe2_t *out);
+int pcgb_ebe2_destroy(pcgb_ebe2_t E);
+int pcgb_ebe2_apply(pcgb_ebe2_t E, const double *d_x, double *d_y, void *stream);
+int pcgb_ebe2_launches(pcgb_ebe2_t E); /* kernel launches per application */
 
 /* ---------------------------------------------------------------- structured hex generator
  * On-device generator of the sub-assembled stiffness matrix of one box of trilinear hex

@@ -75,6 +75,10 @@ SIGNATURES = {
     "pcgb_ebe_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_ebe_bytes": (c_int64, [c_void_p]),
     "pcgb_solver_create_ebe": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "pcgb_ebe2_create": (c_int, [c_int64, c_int, POINTER(EbeGroup), POINTER(c_int32), POINTER(c_void_p)]),
+    "pcgb_ebe2_destroy": (c_int, [c_void_p]),
+    "pcgb_ebe2_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcgb_ebe2_launches": (c_int, [c_void_p]),
     "pcgb_hex_nrows": (c_int64, [POINTER(HexBox)]),
     "pcgb_hex_count": (c_int, [POINTER(HexBox), c_void_p, c_void_p]),
     "pcgb_hex_fill": (c_int, [POINTER(HexBox), POINTER(c_double), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),

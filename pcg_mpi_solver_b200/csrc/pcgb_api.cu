@@ -10,6 +10,7 @@
 #include "comm.cuh"
 #include "hexgen.cuh"
 #include "ebe.cuh"
+#include "ebe_color.cuh"
 
 using namespace pcgb;
 
@@ -19,6 +20,10 @@ struct pcgb_csr_s {
 
 struct pcgb_ebe_s {
   EbePlan P;
+};
+
+struct pcgb_ebe2_s {
+  EbeColorPlan C;
 };
 
 struct GraphKey {
@@ -349,6 +354,105 @@ int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream) {
 }
 
 int64_t pcgb_ebe_bytes(pcgb_ebe_t E) { return E ? E->P.bytes : 0; }
+
+// ------------------------------------------------------------------------------------ coloured EBE operator (round-2 prep)
+// groups[] holds one entry per (pattern group, colour), sorted by colour; phase[g] is the colour.  Pattern matrices of
+// the 24-dof groups are de-duplicated into the constant-memory slots by content of ke_host (same pointer = same slot).
+int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const int32_t *phase, pcgb_ebe2_t *out) {
+  if (!out || n < 0 || ngroups < 0 || (ngroups > 0 && (!groups || !phase))) return fail(PCGB_ERR_ARG, "pcgb_ebe2_create: bad argument");
+  if (n >= (1 << 30)) return fail(PCGB_ERR_ARG, "pcgb_ebe2_create: more than 2^30 dofs");
+  PCGB_TRY(require_device());
+  for (int g = 1; g < ngroups; ++g)
+    if (phase[g] < phase[g - 1]) return fail(PCGB_ERR_ARG, "pcgb_ebe2_create: groups must be sorted by phase (colour)");
+  pcgb_ebe2_t E = new pcgb_ebe2_s();
+  EbePlan &P = E->C.P;
+  P.n = n;
+  P.bytes = 16 * n;
+  std::vector<const double *> slot_key;
+  std::vector<int> blk_group;
+  std::vector<int64_t> blk_e0;
+  std::vector<std::pair<const double *, double *>> ke_dev;   // host pointer -> device copy (shared between colours)
+  int open_warp_phase = -1, open_warp_begin = 0;
+  auto flush_warp = [&]() {
+    if (open_warp_phase >= 0 && (int)blk_group.size() > open_warp_begin) E->C.launches.push_back({1, open_warp_begin, (int)blk_group.size()});
+    open_warp_phase = -1;
+  };
+  for (int g = 0; g < ngroups; ++g) {
+    const pcgb_ebe_group &src = groups[g];
+    if (src.nd <= 0 || src.nd > 96 || src.ne < 0 || !src.ke_host || (src.ne > 0 && (!src.d_idx || !src.d_ck))) {
+      delete E;
+      return fail(PCGB_ERR_ARG, "pcgb_ebe2_create: group %d: pattern size must be 1..96 and arrays non-null", g);
+    }
+    EbeGroup eg;
+    eg.nd = src.nd; eg.ne = src.ne; eg.idx = src.d_idx; eg.sign = src.d_sign; eg.ck = src.d_ck;
+    double *dke = nullptr;
+    for (auto &kv : ke_dev) if (kv.first == src.ke_host) dke = kv.second;
+    if (!dke) {
+      PCGB_CUDA(cudaMalloc(&dke, (size_t)src.nd * src.nd * sizeof(double)));
+      PCGB_CUDA(cudaMemcpy(dke, src.ke_host, (size_t)src.nd * src.nd * sizeof(double), cudaMemcpyHostToDevice));
+      ke_dev.push_back({src.ke_host, dke});
+    }
+    eg.ke = dke;
+    bool t24 = false;
+    if (src.nd == 24) {
+      int slot = -1;
+      for (size_t k = 0; k < slot_key.size(); ++k) if (slot_key[k] == src.ke_host) slot = (int)k;
+      if (slot < 0 && (int)slot_key.size() < kEbeMaxSlots) {
+        slot = (int)slot_key.size();
+        PCGB_CUDA(cudaMemcpyToSymbol(c_ebe_ke24, src.ke_host, 576 * sizeof(double), (size_t)slot * 576 * sizeof(double)));
+        slot_key.push_back(src.ke_host);
+      }
+      if (slot >= 0) { eg.slot = slot; t24 = true; }
+    }
+    if (t24) {
+      if (open_warp_phase >= 0 && open_warp_phase != phase[g]) flush_warp();
+      if (src.ne > 0) E->C.launches.push_back({0, (int)P.groups.size(), 0});
+    } else {
+      if (open_warp_phase >= 0 && open_warp_phase != phase[g]) flush_warp();
+      if (open_warp_phase < 0) { open_warp_phase = phase[g]; open_warp_begin = (int)blk_group.size(); }
+      for (int64_t e0 = 0; e0 < src.ne; e0 += kEbeWarpsPerBlock) { blk_group.push_back((int)P.groups.size()); blk_e0.push_back(e0); }
+    }
+    P.bytes += src.ne * ((int64_t)src.nd * (4 + (src.d_sign ? 1 : 0)) + 8);
+    P.groups.push_back(eg);
+    E->C.nphases = phase[g] + 1;
+  }
+  flush_warp();
+  // a t24 launch of phase c and a warp launch of the same phase may touch the same dofs only if the colouring was
+  // done per pattern group; the Python side colours ALL elements of the subdomain together, so they cannot.
+  if (!P.groups.empty()) {
+    PCGB_CUDA(cudaMalloc(&P.d_groups, P.groups.size() * sizeof(EbeGroup)));
+    PCGB_CUDA(cudaMemcpy(P.d_groups, P.groups.data(), P.groups.size() * sizeof(EbeGroup), cudaMemcpyHostToDevice));
+  }
+  P.nblk_warp = (int)blk_group.size();
+  if (P.nblk_warp > 0) {
+    PCGB_CUDA(cudaMalloc(&P.d_blk_group, blk_group.size() * sizeof(int)));
+    PCGB_CUDA(cudaMalloc(&P.d_blk_e0, blk_e0.size() * sizeof(int64_t)));
+    PCGB_CUDA(cudaMemcpy(P.d_blk_group, blk_group.data(), blk_group.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PCGB_CUDA(cudaMemcpy(P.d_blk_e0, blk_e0.data(), blk_e0.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  }
+  *out = E;
+  return PCGB_OK;
+}
+
+int pcgb_ebe2_destroy(pcgb_ebe2_t E) {
+  if (!E) return PCGB_OK;
+  std::vector<const double *> freed;
+  for (EbeGroup &g : E->C.P.groups) {
+    bool done = false;
+    for (const double *f : freed) done |= (f == g.ke);
+    if (!done) { cudaFree(const_cast<double *>(g.ke)); freed.push_back(g.ke); }
+  }
+  cudaFree(E->C.P.d_groups); cudaFree(E->C.P.d_blk_group); cudaFree(E->C.P.d_blk_e0);
+  delete E;
+  return PCGB_OK;
+}
+
+int pcgb_ebe2_apply(pcgb_ebe2_t E, const double *d_x, double *d_y, void *stream) {
+  if (!E || !d_x || !d_y) return fail(PCGB_ERR_ARG, "pcgb_ebe2_apply: null argument");
+  return ebe_color_apply(E->C, d_x, d_y, (cudaStream_t)stream);
+}
+
+int pcgb_ebe2_launches(pcgb_ebe2_t E) { return E ? (int)E->C.launches.size() : 0; }
 
 // ------------------------------------------------------------------------------------ solver
 static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pcgb_comm_t comm, pcgb_solver_t *out) {

@@ -1,0 +1,46 @@
+"""ROUND-2 PREPARATION: coloured (atomics-free, deterministic) EBE operator.  Written at the end of round 1 with no
+GPU time left; runs only with PCGB_EXPERIMENTAL=1 so that unverified kernels cannot disturb the verified suite."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.hex_mdf import write_hex_mdf
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PCGB_EXPERIMENTAL") != "1", reason="unverified round-2 preparation (PCGB_EXPERIMENTAL=1 to run)")]
+
+
+def test_colored_ebe_matches_csr_and_is_bit_reproducible(cuda, tmp_path):
+    import torch
+    from pcg_mpi_solver_b200.ebe import EbeMatrix, EbeMatrixColored
+    from pcg_mpi_solver_b200.model import load_mdf
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    write_hex_mdf(str(tmp_path), (9, 7, 5))
+    sub = partition_mesh(load_mdf(str(tmp_path)), 1, assemble=True)[0]
+    C = EbeMatrixColored(sub.groups, sub.loc_dof_eff, sub.ndof, device=cuda)
+    x = np.random.default_rng(0).standard_normal(sub.n)
+    xd = torch.from_numpy(x).to(cuda)
+    y = C.apply_local(xd).clone()
+    yref = sub.A @ x
+    assert np.abs(y.cpu().numpy() - yref).max() <= 1e-12 * (abs(sub.A) @ np.abs(x)).max()
+    for _ in range(5):
+        assert torch.equal(C.apply_local(xd), y)          # fixed summation order: bit-identical
+    assert C.launches() == C.ncolors                       # one pattern group -> one launch per colour
+
+
+def test_colored_ebe_concrete(cuda):
+    import torch
+    from pcg_mpi_solver_b200.ebe import EbeMatrixColored
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    zp = os.path.join(root, "oracle", "_ref", "concrete.zip")
+    if not os.path.exists(zp):
+        pytest.skip("concrete.zip not staged")
+    sub = partition_mesh(zp, 1, assemble=False)[0]
+    csr = sub.to_operator(device=cuda, kind="csr")
+    C = EbeMatrixColored(sub.groups, sub.loc_dof_eff, sub.ndof, device=cuda)
+    x = torch.randn(sub.n, dtype=torch.float64, device=cuda)
+    ye, yc = C.apply_local(x).clone(), csr.apply(x)
+    assert float((ye - yc).abs().max() / yc.abs().max()) <= 1e-12
+    assert torch.equal(C.apply_local(x), ye)
