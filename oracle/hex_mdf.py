@@ -12,9 +12,11 @@ import scipy.io
 from .ref_pcg import hex_ke
 
 
-def write_hex_mdf(path, ng, E=1.0, nu=0.3, h=None, traction=1.0):
+def write_hex_mdf(path, ng, E=1.0, nu=0.3, h=None, traction=1.0, pull=None):
     """Hex mesh of ng elements, clamped at global x index 0, -z traction on x = max.  Returns a dict of
-    the arrays written (global numbering: node = (gz*(ny+1)+gy)*(nx+1)+gx, dof = 3*node+dir)."""
+    the arrays written (global numbering: node = (gz*(ny+1)+gy)*(nx+1)+gx, dof = 3*node+dir).
+    pull=d: displacement-controlled variant - the x = max face is ALSO fixed, with prescribed displacement
+    Ud = (d, 0, 0), and there is no traction (exercises Fext = F*delta - K (Ud*delta), pcg_solver.py:226-238)."""
     os.makedirs(path, exist_ok=True)
     nx, ny, nz = ng
     h = 1.0 / nx if h is None else h
@@ -59,12 +61,18 @@ def write_hex_mdf(path, ng, E=1.0, nu=0.3, h=None, traction=1.0):
     cy = np.where((gy == 0) | (gy == ny), 0.5, 1.0)
     cz = np.where((gz == 0) | (gz == nz), 0.5, 1.0)
     F[3 * np.nonzero(face)[0] + 2] = (-traction * h * h * cy * cz)[face]
+    Ud = np.zeros(ndof)
     fixed_nodes = np.nonzero(gx == 0)[0]
+    if pull is not None:
+        F[:] = 0.0
+        pulled = np.nonzero(gx == nx)[0]
+        Ud[3 * pulled] = pull
+        fixed_nodes = np.concatenate([fixed_nodes, pulled])
     fixed = np.sort((3 * fixed_nodes[:, None] + np.arange(3)[None, :]).ravel())
     eff = np.setdiff1d(np.arange(ndof), fixed)
     wbin("DiagM", np.ones(ndof), np.float64)
     wbin("F", F, np.float64)
-    wbin("Ud", np.zeros(ndof), np.float64)
+    wbin("Ud", Ud, np.float64)
     wbin("Vd", np.zeros(0), np.float64)
     wbin("NodeCoordVec", coords, np.float64)
     wbin("DofEff", eff, np.int32)
@@ -81,4 +89,4 @@ def write_hex_mdf(path, ng, E=1.0, nu=0.3, h=None, traction=1.0):
     mat = np.zeros((1,), dtype=[("E", "O"), ("Pos", "O"), ("Rho", "O")])
     mat[0] = (np.array([[E]]), np.array([[nu]]), np.array([[1.0]]))
     scipy.io.savemat(os.path.join(path, "MatProp.mat"), {"Data": mat})
-    return {"F": F, "eff": eff, "fixed": fixed, "nodes": nodes, "ndof": ndof, "ne": ne, "h": h}
+    return {"F": F, "Ud": Ud, "eff": eff, "fixed": fixed, "nodes": nodes, "ndof": ndof, "ne": ne, "h": h}
