@@ -77,9 +77,11 @@ class _Ranks:
         if self.size > 1:
             import torch
             import torch.distributed as dist
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
+            backend = os.environ.get("PCGB_DIST_BACKEND", "nccl")   # "gloo": CPU tests of the multi-rank host logic
+            if backend == "nccl":
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)))
             if not dist.is_initialized():
-                dist.init_process_group("nccl")
+                dist.init_process_group(backend)
             self.dist = dist
 
     def gather(self, obj):

@@ -92,3 +92,85 @@ def test_builder_rhs_and_cli_reproduce_reference_ramp_cpu(gold, tmp_path):
         ref = arr[f"U{frame}_p1"]
         assert np.linalg.norm(u - ref) <= 1e-12 * np.linalg.norm(ref)
         assert np.allclose(u[3 * np.nonzero(info["Ud"][0::3])[0]], meta["pull"] * meta["deltas"][frame])   # prescribed dofs carry Ud*delta
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# world_size-2 gloo test of the MULTI-RANK host logic of the file-compatible stage: per-rank fixtures, the interface
+# sum of K (Ud delta) across ranks, result files written by two ranks at gathered offsets (file_operations.py:348-375)
+class _GlooComm:
+    """Reductions / interface exchange of the CPU checker over torch.distributed (gloo); sums in rank order."""
+
+    def __init__(self, dist):
+        self.dist, self.rank, self.size = dist, dist.get_rank(), dist.get_world_size()
+
+    def allreduce(self, v):
+        box = [None] * self.size
+        self.dist.all_gather_object(box, np.atleast_1d(np.asarray(v, dtype=float)))
+        tot = box[0]
+        for b in box[1:]:
+            tot = tot + b
+        return float(tot[0]) if np.ndim(v) == 0 else tot
+
+    def exchange_add_full(self, part, y):
+        box = [None] * self.size
+        self.dist.all_gather_object(box, {nb: y[idx].copy() for nb, idx in zip(part.nbr, part.ovrlp_full)})
+        for nb, idx in zip(part.nbr, part.ovrlp_full):
+            y[idx] += box[nb][self.rank]
+        return y
+
+
+def _gloo_backend(mp, ranks):
+    from pcg_mpi_solver_b200.partition import SubdomainData, TypeGroup
+    comm = _GlooComm(ranks.dist)
+    part = R.EbePart(mp)
+    groups = [TypeGroup(int(g["ElemTypeId"]), g["ElemList_LocDofVector"], g["ElemList_SignVector"], g["ElemList_Ck"], g["ElemStiffMat"], None)
+              for g in mp["SubDomainData"]["StrucDataList"]]
+    sub = SubdomainData(int(mp["Id"]), ranks.size, np.asarray(mp["DofVector"]), np.asarray(mp["NodeIdVector"]), part.eff, groups,
+                        part.nbr, part.ovrlp_full, [], np.asarray(mp["DofWeightVector"], dtype=float),
+                        np.asarray(mp["RefLoadVector"], dtype=float), np.asarray(mp["Ud"], dtype=float),
+                        int(mp["GlobData"]["GlobNDofEff"]), int(mp["GlobData"]["GlobNDof"]))
+    minv = R.Operator([part], comm).jacobi()
+
+    def solve_step(b, x0, tol, maxiter):
+        part.b, part.x0 = b, x0
+        out = R.ref_pcg([part], minv, tol, maxiter, nglob=sub.n_global_eff, comm=comm)
+        return out["X"][0], out["Flag"], out["RelRes"], out["Iter"]
+
+    return sub, solve_step
+
+
+def _cli_rank(rank, world, port, work, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PCGB_DIST_BACKEND="gloo")
+    from pcg_mpi_solver_b200.pcg_solver import run
+    out = run(2, 0, workdir=work, backend=_gloo_backend, quiet=True)
+    q.put((rank, [int(v) for v in out["Iter"]], [int(v) for v in out["Flag"]]))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cli_two_ranks_gloo_reproduce_reference_two_part_run(gold, tmp_path):
+    import torch.multiprocessing as tmp_mp
+    from pcg_mpi_solver_b200.partition import build_subdomains
+    from pcg_mpi_solver_b200.pcg_solver import export_mesh_parts
+    meta, arr = gold
+    model, info = _model(tmp_path, meta)
+    subs = build_subdomains(model, arr["elepart_2"].astype(np.int64), 2, assemble=False)
+    work = _workdir(tmp_path, meta)
+    export_mesh_parts(os.path.join(work, "data", "ModelData", "MPI") + "/", subs)
+    ctx = tmp_mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cli_rank, args=(r, 2, 29433, work, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    run2 = meta["runs"]["p2"]
+    assert res[0][1] == run2["Iter"] and res[0][2] == [0, 0, 0]      # rank 0 keeps the per-step records (:593-596)
+    for frame in (1, 2):
+        _, u = rr.read_results(work, "hexpull", 2, 2, info["ndof"], frame=frame)   # one file written by both ranks
+        ref = arr[f"U{frame}_p2"]
+        assert np.linalg.norm(u - ref) <= 1e-11 * np.linalg.norm(ref)
