@@ -93,6 +93,7 @@ class SubdomainData:
         reads - what oracle.ref_pcg.EbePart and a reference-side binding consume."""
         groups = [{"ElemTypeId": g.type_id, "ElemList_LocDofVector": g.loc_dof, "ElemList_LocDofVector_Flat": g.loc_dof.flatten(),
                    "ElemList_SignVector": g.sign, "ElemList_Ck": g.ck, "ElemStiffMat": g.ke, "ElemDiagStiffMat": np.diag(g.ke).copy(),
+                   "ElemList_LocNodeIdVector": g.loc_dof[0::3, :] // 3,      # local node ids (3 dofs per node, partition_mesh.py:454)
                    "ElemList_LocElemId": None, "N_Elem": g.ck.size} for g in self.groups]
         flat = np.concatenate([g["ElemList_LocDofVector_Flat"] for g in groups]) if groups else np.zeros(0, dtype=np.int64)
         return {"Id": self.id, "NDOF": self.ndof, "NNode": self.node_ids.size, "DofVector": self.dof_vector, "NodeIdVector": self.node_ids,

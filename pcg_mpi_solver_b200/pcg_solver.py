@@ -55,6 +55,9 @@ def export_mesh_parts(prefix: str, subs, glob_extra=None):
     for s in subs:
         mp_ = s.to_refmeshpart()
         mp_["NodeWeightVector"] = mp_["DofWeightVector"][0::3].copy()
+        # keys the reference's OWN solver stage reads besides the hot-path ones (pcg_solver.py:144-148, 365, 901-902)
+        mp_["RefPlotData"] = {"TestPlotFlag": False, "J": [], "LocalDofVec": [], "DofVec": np.zeros(0, dtype=int), "RefPlotDofVec": [], "qpoint": []}
+        mp_["MPList_RefPlotDofIndicesList"] = []
         mp_["GlobData"].update(glob_extra or {})
         mp_["GlobData"].setdefault("dt", 0.0)
         bufs.append(np.frombuffer(zlib.compress(pickle.dumps(mp_, pickle.HIGHEST_PROTOCOL)), "b"))

@@ -127,3 +127,28 @@ def test_cli_on_gpu_matches_reference_golden(cuda, tmp_path):
     run1 = meta["runs"]["box1"]
     assert res["Flag"] == 0 and abs(res["Iter"] - run1["Iter"]) <= 2 and res["RelRes"] <= meta["tol"]
     assert np.linalg.norm(u - gold["U_box1"]) <= 1e-8 * np.linalg.norm(gold["U_box1"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/solver/pcg_solver.py"), reason="needs the reference checkout")
+@pytest.mark.parametrize("nparts", [1, 2])
+def test_reference_solver_consumes_the_product_builders_fixture(tmp_path, nparts):
+    """Drop-in the other way round: the UNMODIFIED reference solver (pcg_solver.py under the fake-MPI shim) runs on the
+    fixture written by the product's partition_mesh()/export_mesh_parts() and reproduces its own golden run."""
+    from pcg_mpi_solver_b200.hexmesh import block_grid, partition_blocks
+    from pcg_mpi_solver_b200.model import load_mdf
+    from pcg_mpi_solver_b200.partition import partition_mesh
+    from pcg_mpi_solver_b200.pcg_solver import export_mesh_parts
+    with open(os.path.join(GOLD, "hex_ref.json")) as f:
+        meta = json.load(f)
+    gold = np.load(os.path.join(GOLD, "hex_ref.npz"))
+    ng = tuple(meta["ng"])
+    work, mdf, info = _setup_workdir(tmp_path, ng, meta["tol"], meta["maxiter"])
+    case = "box1" if nparts == 1 else "box2"
+    ep = gold[f"elepart_{case}"].astype(np.int64) if nparts > 1 else None
+    subs = partition_mesh(load_mdf(mdf, "hexmodel"), nparts, elepart=ep, assemble=False)
+    export_mesh_parts(os.path.join(work, "data", "ModelData", "MPI") + "/", subs)
+    rr.solve_stage(work, nparts, run_id=5)                      # /root/reference/src/solver/pcg_solver.py, one process per part
+    res, u = rr.read_results(work, "hexmodel", nparts, 5, info["ndof"])
+    run = meta["runs"][case]
+    assert res["Flag"] == 0 and res["Iter"] == run["Iter"]
+    assert np.linalg.norm(u - gold[f"U_{case}"]) <= 1e-12 * np.linalg.norm(gold[f"U_{case}"])
