@@ -25,10 +25,10 @@
 extern "C" {
 #endif
 
-#define PCGB_VERSION 100 /* 0.1.0 */
+#define PCGB_VERSION 200 /* 0.2.0 */
 
 typedef struct pcgb_csr_s *pcgb_csr_t;     /* device CSR matrix + merge-path SpMV plan          */
-typedef struct pcgb_comm_s *pcgb_comm_t;   /* NCCL communicator (one rank = one GPU)            */
+typedef struct pcgb_comm_s *pcgb_comm_t;   /* communicator: peer-memory windows (+ NCCL), one rank = one GPU */
 typedef struct pcgb_halo_s *pcgb_halo_t;   /* interface ("halo") exchange-add plan              */
 typedef struct pcgb_solver_s *pcgb_solver_t; /* PCG workspace bound to one operator             */
 typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-by-element operator */
@@ -40,6 +40,7 @@ typedef struct pcgb_ebe2_s *pcgb_ebe2_t;   /* round-2 preparation: coloured (ato
 #define PCGB_ERR_CUDA (-2)
 #define PCGB_ERR_NCCL (-3)
 #define PCGB_ERR_NODEVICE (-4)
+#define PCGB_ERR_COMM (-5) /* a peer-memory exchange timed out waiting for another rank */
 
 int pcgb_version(void);
 /* sizeof(pcgb_options), sizeof(pcgb_result), sizeof(pcgb_hex_box), sizeof(pcgb_ebe_group): lets a binding verify its struct layouts */
@@ -62,14 +63,25 @@ int pcgb_csr_destroy(pcgb_csr_t A);
 int pcgb_spmv(pcgb_csr_t A, const double *d_x, double *d_y, void *stream);
 /* d[i] = A[i,i]  (Jacobi diagonal, replaces calcMatVecProd(...,'Preconditioner'), pcg_solver.py:282-287) */
 int pcgb_csr_diag(pcgb_csr_t A, double *d_diag, void *stream);
+/* The persistent staged-x SpMV kernel reads its own 16-bit index stream, never d_col.  pcgb_csr_release_col caches the
+ * diagonal and drops the library's reference to d_col; the caller may then free it (2 GB at 128^3, 16 GB at 256^3).
+ * PCGB_ERR_ARG when the selected kernel still needs the column array. */
+int pcgb_csr_release_col(pcgb_csr_t A, void *stream);
+/* Interface-first split of the SpMV for the multi-GPU overlap ("order boundary rows first, launch exchange,
+ * compute interior rows"): d_rows = distinct local rows taking part in the interface exchange (pcg_solver.py:304-312).
+ * Tiles owning such a row run in a first launch, all others in a second one.  pcgb_solver_create registers the rows
+ * of its halo plan itself; these two entry points make the split testable on one GPU.  d_out_dot (may be NULL) = x.y */
+int pcgb_csr_set_boundary_rows(pcgb_csr_t A, const int32_t *d_rows, int64_t count, void *stream);
+int pcgb_spmv_split(pcgb_csr_t A, const double *d_x, double *d_y, double *d_out_dot, void *stream);
 /* Algorithmic bytes of one SpMV: 12*nnz + R*(nrows+1) + 8*ncols + 8*nrows. */
 int64_t pcgb_spmv_bytes(pcgb_csr_t A);
 /* Bytes the selected kernel really streams from HBM (the staged-x kernel reads 16-bit local column
- * indices: 10 B per non-zero instead of 12). */
+ * indices: 10 B per non-zero instead of 12; with the column-triple index 8 + 2/3 B). */
 int64_t pcgb_spmv_stream_bytes(pcgb_csr_t A);
 /* plan introspection for tests / DESIGN.md: tiles, tile items, lanes, snap, split rows, smem bytes,
- * max row, tma, staged, x windows, staged doubles per tile (cap), max windows per tile */
-int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[12]);
+ * max row, tma, staged, x windows, staged doubles per tile (cap), max windows per tile, column-triple index (0/1),
+ * interface tiles (-1 = no split registered), resident CTAs of the persistent kernel, column array released (0/1) */
+int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[16]);
 
 /* ---------------------------------------------------------------- vector kernels (a4-a10)
  * out[0] = sum_i a[i]*b[i]*w[i]   (w may be NULL = all ones).  np.dot(a, b*w) of
@@ -83,14 +95,28 @@ int pcgb_mul(int64_t n, const double *d_x, const double *d_y, double *d_z, void 
 int pcgb_reciprocal(int64_t n, const double *d_d, double *d_out, void *stream);
 
 /* ---------------------------------------------------------------- communicator (a13)
- * Replaces mpi4py COMM_WORLD (pcg_solver.py:968-970).  NCCL is resolved at run time with
- * dlopen("libnccl.so.2") so the library loads on a box without NCCL.  Rank 0 obtains a
- * unique id and the host code broadcasts it (torch.distributed / any side channel).      */
+ * Replaces mpi4py COMM_WORLD (pcg_solver.py:968-970).  Two transports for the data path:
+ *   PEER (default)  the library's own kernels over CUDA-IPC mapped peer memory (NVLink / NVSwitch): the all-reduce is
+ *                   fused into the reduction kernel of the iteration, the halo values are stored straight into the
+ *                   neighbours' receive buffers (csrc/peer.cuh).  Needs the window exchange below.
+ *   NCCL            ncclAllReduce / ncclSend / ncclRecv (baseline and fallback; PCGB_COMM=nccl selects it).
+ * NCCL is resolved at run time with dlopen("libnccl.so.2") so the library loads on a box without NCCL.  Rank 0 obtains a
+ * unique id and the host code broadcasts it (torch.distributed / mpi4py / any side channel).  id == NULL creates a
+ * peer-only communicator (no NCCL at all; at most 16 ranks).                                                     */
 #define PCGB_UNIQUE_ID_BYTES 128
+#define PCGB_IPC_BLOB_BYTES 64
+#define PCGB_TRANSPORT_NCCL 0
+#define PCGB_TRANSPORT_PEER 1
 int pcgb_comm_unique_id(unsigned char id[PCGB_UNIQUE_ID_BYTES]);
-int pcgb_comm_create(int rank, int nranks, const unsigned char id[PCGB_UNIQUE_ID_BYTES], pcgb_comm_t *out);
+int pcgb_comm_create(int rank, int nranks, const unsigned char *id /* [PCGB_UNIQUE_ID_BYTES] or NULL */, pcgb_comm_t *out);
 int pcgb_comm_destroy(pcgb_comm_t c);
-/* in-place sum of `count` doubles over all ranks (MPI_SUM, pcg_solver.py:622-628) */
+/* window exchange: export -> all-gather the blobs over the host side channel (rank order) -> import */
+int pcgb_comm_window_export(pcgb_comm_t c, unsigned char blob[PCGB_IPC_BLOB_BYTES]);
+int pcgb_comm_window_import(pcgb_comm_t c, const unsigned char *blobs /* nranks * PCGB_IPC_BLOB_BYTES */);
+int pcgb_comm_transport(pcgb_comm_t c);                  /* transport the data path uses right now */
+int pcgb_comm_set_transport(pcgb_comm_t c, int transport);
+int pcgb_comm_status(pcgb_comm_t c, void *stream);       /* 0 healthy; != 0 after a peer exchange timed out (sticky) */
+/* in-place sum of `count` doubles over all ranks (MPI_SUM, pcg_solver.py:622-628); rank-ordered, bit-identical on every rank */
 int pcgb_allreduce_sum(pcgb_comm_t c, double *d_buf, int count, void *stream);
 
 /* ---------------------------------------------------------------- halo exchange-add (a14)
@@ -105,6 +131,11 @@ int pcgb_allreduce_sum(pcgb_comm_t c, double *d_buf, int count, void *stream);
 int pcgb_halo_create(pcgb_comm_t c, int n_nbr, const int32_t *nbr_rank, const int64_t *nbr_ptr,
                      const int64_t *idx_host, int64_t nlocal, pcgb_halo_t *out);
 int pcgb_halo_destroy(pcgb_halo_t h);
+/* peer transport: every rank exports its receive block, the host all-gathers the blobs (pcgb_halo_blob_bytes each, rank
+ * order) and imports them; the import checks that both sides of every interface list the same number of shared dofs */
+int64_t pcgb_halo_blob_bytes(pcgb_halo_t h);
+int pcgb_halo_export(pcgb_halo_t h, unsigned char *blob);
+int pcgb_halo_import(pcgb_halo_t h, const unsigned char *blobs);
 /* y[idx] += (values of the same dofs on the neighbours) */
 int pcgb_halo_exchange_add(pcgb_halo_t h, double *d_y, void *stream);
 int64_t pcgb_halo_bytes(pcgb_halo_t h); /* bytes sent (= received) per exchange by this rank */
@@ -122,6 +153,7 @@ typedef struct pcgb_options {
   int32_t fixed_iters;  /* benchmark mode: ignore convergence, run exactly maxiter iterations */
   int32_t record_resvec; /* keep ||r|| per iteration (reference has this commented out, :428-434) */
   int32_t time_kernels; /* bracket every SpMV launch of the loop with CUDA events (forces direct launches) */
+  int32_t x0_zero;      /* the caller guarantees d_x is all zeros on entry: r0 = b exactly, the initial operator application is skipped */
 } pcgb_options;
 
 typedef struct pcgb_result {
@@ -139,6 +171,8 @@ typedef struct pcgb_result {
   double spmv_ms;     /* sum of the SpMV launch durations inside the loop (time_kernels only)        */
   int64_t spmv_timed; /* number of SpMV launches in spmv_ms                                         */
   int64_t loop_iters; /* iterations executed inside the timed loop                                  */
+  double setup_ms;    /* device time from the entry of the solve to the start of the loop (||b||, r0, rho0) */
+  double final_ms;    /* device time from the end of the loop to the copy-out of x (finalisation matvec)    */
 } pcgb_result;
 
 int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,

@@ -194,7 +194,8 @@ def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True, 
         nglob = int(round(sum(float(w.sum()) for w in W)))
     Fext = [np.array(p.b, dtype=float) for p in parts]                 # :377
     X = [np.array(p.x0, dtype=float) for p in parts]                   # :378-379
-    XMin = [x for x in X]                                              # :380
+    XMin = [x for x in X]                                              # :380  MP_XMin = MP_X: the SAME array ...
+    aliased = True                                                     # ... until the first np.array(MP_X) copy (:557)
     n2b = np.sqrt(_mpi_sum([np.dot(Fext[k], Fext[k] * W[k]) for k in rng]))  # :381-383
     tolb = tol * n2b                                                   # :384
     if n2b == 0:                                                       # :387-395 (returns the initial guess)
@@ -253,7 +254,9 @@ def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True, 
             stag += 1
         else:
             stag = 0
-        X = [X[k] + alpha * Pv[k] for k in rng]                        # :516 (new arrays: XMin keeps old ones)
+        X = [X[k] + alpha * Pv[k] for k in rng]                        # :516 in place in the reference, so an XMin that is
+        if aliased:                                                    #      still bound to MP_X follows the update
+            XMin = X
         normr_act = normr                                              # :518
         if resvec is not None:
             resvec.append(normr)
@@ -278,6 +281,7 @@ def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True, 
         if normr_act < normrmin:                                       # :555-558
             normrmin = normr_act
             XMin = [np.array(x) for x in X]
+            aliased = False
             imin = i
         if stag >= maxstag:                                            # :560-562
             flag = 3
@@ -298,7 +302,7 @@ def ref_pcg(parts, minv, tol, maxiter, nglob=None, resvec=None, exist_dp0=True, 
         Xout = XMin                                                    # :569 + :598: Un is built from XMin
     it += 1                                                            # :584
     return dict(X=Xout, Flag=flag, RelRes=float(relres), Iter=int(it), iMin=imin, matvecs=op.matvecs,
-                normb=float(n2b), too_small_tol=too_small, stag=stag, moresteps=moresteps)
+                normb=float(n2b), too_small_tol=too_small, stag=stag, moresteps=moresteps, aliased=aliased)
 
 
 # ----------------------------------------------------------------------------------------- test problems

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpcgb200.so")
 
 UNIQUE_ID_BYTES = 128
+IPC_BLOB_BYTES = 64
+TRANSPORT_NCCL, TRANSPORT_PEER = 0, 1
 
 
 class PcgbError(RuntimeError):
@@ -23,14 +25,14 @@ class PcgbError(RuntimeError):
 class Options(ctypes.Structure):
     _fields_ = [("tol", c_double), ("maxiter", c_int32), ("n_global", c_int64), ("max_stag", c_int32),
                 ("check_every", c_int32), ("use_graph", c_int32), ("fixed_iters", c_int32),
-                ("record_resvec", c_int32), ("time_kernels", c_int32)]
+                ("record_resvec", c_int32), ("time_kernels", c_int32), ("x0_zero", c_int32)]
 
 
 class Result(ctypes.Structure):
     _fields_ = [("flag", c_int32), ("iters", c_int32), ("relres", c_double), ("normb", c_double),
                 ("imin", c_int32), ("stag", c_int32), ("moresteps", c_int32), ("too_small_tol", c_int32),
                 ("matvecs", c_int64), ("launches", c_int64), ("loop_ms", c_double), ("spmv_ms", c_double),
-                ("spmv_timed", c_int64), ("loop_iters", c_int64)]
+                ("spmv_timed", c_int64), ("loop_iters", c_int64), ("setup_ms", c_double), ("final_ms", c_double)]
 
 
 class EbeGroup(ctypes.Structure):
@@ -51,6 +53,9 @@ SIGNATURES = {
     "pcgb_csr_destroy": (c_int, [c_void_p]),
     "pcgb_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_csr_diag": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pcgb_csr_release_col": (c_int, [c_void_p, c_void_p]),
+    "pcgb_csr_set_boundary_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcgb_spmv_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_spmv_bytes": (c_int64, [c_void_p]),
     "pcgb_spmv_stream_bytes": (c_int64, [c_void_p]),
     "pcgb_csr_plan_info": (c_int, [c_void_p, POINTER(c_int64)]),
@@ -61,9 +66,17 @@ SIGNATURES = {
     "pcgb_comm_unique_id": (c_int, [POINTER(c_ubyte)]),
     "pcgb_comm_create": (c_int, [c_int, c_int, POINTER(c_ubyte), POINTER(c_void_p)]),
     "pcgb_comm_destroy": (c_int, [c_void_p]),
+    "pcgb_comm_window_export": (c_int, [c_void_p, POINTER(c_ubyte)]),
+    "pcgb_comm_window_import": (c_int, [c_void_p, POINTER(c_ubyte)]),
+    "pcgb_comm_transport": (c_int, [c_void_p]),
+    "pcgb_comm_set_transport": (c_int, [c_void_p, c_int]),
+    "pcgb_comm_status": (c_int, [c_void_p, c_void_p]),
     "pcgb_allreduce_sum": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "pcgb_halo_create": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_int64), POINTER(c_int64), c_int64, POINTER(c_void_p)]),
     "pcgb_halo_destroy": (c_int, [c_void_p]),
+    "pcgb_halo_blob_bytes": (c_int64, [c_void_p]),
+    "pcgb_halo_export": (c_int, [c_void_p, POINTER(c_ubyte)]),
+    "pcgb_halo_import": (c_int, [c_void_p, POINTER(c_ubyte)]),
     "pcgb_halo_exchange_add": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pcgb_halo_bytes": (c_int64, [c_void_p]),
     "pcgb_solver_create": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),

@@ -76,14 +76,44 @@ class CsrMatrix:
         return int(_lib.load().pcgb_spmv_stream_bytes(self._h))
 
     def plan_info(self) -> dict:
-        info = (ctypes.c_int64 * 12)()
+        info = (ctypes.c_int64 * 16)()
         _lib.check(_lib.load().pcgb_csr_plan_info(self._h, info))
         keys = ["ntiles", "tile_items", "lanes", "snap", "split_rows", "smem_bytes", "max_row", "tma", "staged", "x_windows",
-                "x_cap", "max_windows_per_tile"]
+                "x_cap", "max_windows_per_tile", "triple_index", "interface_tiles", "resident_ctas", "col_released"]
         return dict(zip(keys, [int(v) for v in info]))
+
+    def release_col(self) -> bool:
+        """Free the 4-byte column array when the selected SpMV kernel does not read it (the persistent staged-x kernel
+        streams its own 16-bit indices): 2 GB at 128^3, 16 GB at 256^3.  The diagonal is cached first.  Returns True
+        when the array was released; to_scipy() is not available afterwards."""
+        if self.col is None:
+            return True
+        with torch.cuda.device(self.device):
+            rc = _lib.load().pcgb_csr_release_col(self._h, _lib.stream_ptr())
+        if rc != 0:
+            return False
+        self.col = None
+        return True
+
+    def set_boundary_rows(self, rows: torch.Tensor) -> None:
+        """Register the interface rows (int32 CUDA tensor) for the interface-first split (see pcgb_csr_set_boundary_rows)."""
+        assert rows.is_cuda and rows.dtype == torch.int32
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcgb_csr_set_boundary_rows(self._h, _lib.ptr(rows), rows.numel(), _lib.stream_ptr()),
+                       "pcgb_csr_set_boundary_rows")
+
+    def spmv_split(self, x: torch.Tensor, with_dot: bool = False):
+        """y = A x as two launches (interface tiles first); returns y or (y, x.y)."""
+        y = torch.empty(self.shape[0], dtype=torch.float64, device=self.device)
+        d = torch.zeros(1, dtype=torch.float64, device=self.device) if with_dot else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().pcgb_spmv_split(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(d), _lib.stream_ptr()), "pcgb_spmv_split")
+        return (y, d) if with_dot else y
 
     def to_scipy(self):
         import scipy.sparse as sp
+        if self.col is None:
+            raise _lib.PcgbError("CsrMatrix.to_scipy: the column array was released (release_col)")
         return sp.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()), shape=self.shape)
 
     def __del__(self):

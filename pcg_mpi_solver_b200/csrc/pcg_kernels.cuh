@@ -24,7 +24,9 @@ struct PcgCtrl {
   double tolb, n2b, eps;
   int state, flag, iter, stag, moresteps, imin;
   int xcur, xmin;  // which of the two x buffers holds X / XMin (zero-copy min-residual tracking, :555-558)
-  int maxiter, maxstag, fixed_iters, pad;
+  int maxiter, maxstag, fixed_iters;
+  int alias;       // 1 while XMin is still the SAME array as X: the reference binds MP_XMin = MP_X (pcg_solver.py:379-380)
+                   // and updates MP_X in place (:516), so XMin follows X until the first np.array(MP_X) copy (:557)
 };
 
 constexpr int kVecBlock = 256;
@@ -117,7 +119,7 @@ k_update(const PcgCtrl *__restrict__ ctrl, int64_t n, double *__restrict__ r, co
   __shared__ double red[5 * 32];
   const double alpha = ctrl->alpha;
   const int cur = ctrl->xcur;
-  const int dst = (cur == ctrl->xmin) ? (cur ^ 1) : cur;
+  const int dst = (!ctrl->alias && cur == ctrl->xmin) ? (cur ^ 1) : cur;   // aliased: in place, XMin follows X
   const double *xs = cur ? xb1 : xb0;
   double *xd = dst ? xb1 : xb0;
   double spp = 0.0, sxx = 0.0, srr = 0.0, srz = 0.0, ninf = 0.0;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void ctrl_next(PcgCtrl *c, double rz, double ninf) {
 // tail of an iteration after the norms are known (pcg_solver.py:504-562)
 __device__ __forceinline__ void ctrl_norms(PcgCtrl *c, double pp, double xx, double rr, double rz, double ninf, double *resvec) {
   // the x buffer switch performed by k_update
-  if (c->xcur == c->xmin) c->xcur ^= 1;
+  if (!c->alias && c->xcur == c->xmin) c->xcur ^= 1;
   const double normp = sqrt(pp), normx = sqrt(xx), normr = sqrt(rr);
   c->normp = normp; c->normx = normx; c->normr = normr;
   if (normp * fabs(c->alpha) < c->eps * normx) c->stag += 1;  // :512-513
@@ -192,6 +194,7 @@ __device__ __forceinline__ void ctrl_norms(PcgCtrl *c, double pp, double xx, dou
     c->normrmin = normr;
     c->xmin = c->xcur;
     c->imin = c->iter;
+    c->alias = 0;             // XMin = np.array(MP_X): from here on XMin is a frozen copy
   }
   if (!c->fixed_iters && c->stag >= c->maxstag) { c->flag = 3; c->state = ST_BREAK; return; }  // :560-562
   ctrl_next(c, rz, ninf);
@@ -246,6 +249,9 @@ __global__ void k_ctrl_head(PcgCtrl *ctrl, const double *__restrict__ red /* rz,
   if (advance) ctrl_next(ctrl, red[0], red[1]);
   else ctrl_head(ctrl, red[0], red[1]);
 }
+
+// out[0] = sqrt(in[0])  (ResVec[0] = ||r0|| without a host round trip)
+__global__ void k_sqrt_store(const double *__restrict__ in, double *__restrict__ out) { out[0] = sqrt(in[0]); }
 
 // ---- simple elementwise kernels exposed through the C ABI
 __global__ void k_axpby(int64_t n, double a, const double *__restrict__ x, double b, double *__restrict__ y) {

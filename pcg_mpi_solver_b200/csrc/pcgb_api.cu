@@ -2,6 +2,7 @@
 // sm_100a only.  No CPU fallback: every compute entry point requires a CUDA device.
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -20,10 +21,12 @@ struct pcgb_csr_s {
 
 struct pcgb_ebe_s {
   EbePlan P;
+  int device = 0;
 };
 
 struct pcgb_ebe2_s {
   EbeColorPlan C;
+  int device = 0;
 };
 
 struct GraphKey {
@@ -49,7 +52,7 @@ struct pcgb_solver_s {
   PcgCtrl *h_ctrl = nullptr;    // pinned
   double *h_red = nullptr;      // pinned [8]
   cudaStream_t own = nullptr;   // the solve runs here: the caller's stream may be the legacy stream, which cannot be captured
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_l0 = nullptr, ev_l1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   std::vector<cudaEvent_t> ev_k;  // SpMV brackets (time_kernels)
   cudaGraphExec_t gexec = nullptr;
   GraphKey gkey{nullptr, nullptr, nullptr, nullptr, 0};
@@ -65,6 +68,61 @@ static int require_device() {
   }
   return PCGB_OK;
 }
+
+namespace {
+template <typename T>
+cudaError_t upload(T **d, const std::vector<T> &v) {
+  cudaError_t e = cudaMalloc(d, std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (e != cudaSuccess || v.empty()) return e;
+  return cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+// blob of a halo plan: IPC handle | m | per source rank r: {offset of r's segment in my receive buffer (doubles, -1 = not a
+// neighbour), my neighbour slot of r, number of shared entries}
+struct HaloBlobHead { unsigned char handle[PCGB_IPC_BLOB_BYTES]; int64_t m; };
+struct HaloBlobRank { int64_t off, slot, cnt; };
+}  // namespace
+
+// Constant-memory slots of the 24-dof pattern matrices (c_ebe_ke24) are a per-device resource shared by every EBE
+// operator of the process: slots are de-duplicated by content and reference-counted, so a second operator can never
+// overwrite the matrices of a live one; when all slots are taken the group runs on the warp kernel (Ke from global memory).
+namespace {
+struct EbeSlot { int refs = 0; double ke[576]; };
+struct EbeSlotTable { EbeSlot slot[kEbeMaxSlots]; };
+std::mutex g_ebe_slot_mutex;
+EbeSlotTable *ebe_slot_table(int device) {
+  static std::vector<EbeSlotTable *> tabs;
+  if (device < 0) return nullptr;
+  if ((int)tabs.size() <= device) tabs.resize((size_t)device + 1, nullptr);
+  if (!tabs[(size_t)device]) tabs[(size_t)device] = new EbeSlotTable();
+  return tabs[(size_t)device];
+}
+// returns the slot holding `ke` (acquiring a reference) or -1 when the table is full
+int ebe_slot_acquire(const double *ke) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lock(g_ebe_slot_mutex);
+  EbeSlotTable *t = ebe_slot_table(dev);
+  int free_slot = -1;
+  for (int k = 0; k < kEbeMaxSlots; ++k) {
+    if (t->slot[k].refs > 0 && memcmp(t->slot[k].ke, ke, sizeof(t->slot[k].ke)) == 0) { t->slot[k].refs += 1; return k; }
+    if (t->slot[k].refs == 0 && free_slot < 0) free_slot = k;
+  }
+  if (free_slot < 0) return -1;
+  if (cudaMemcpyToSymbol(c_ebe_ke24, ke, 576 * sizeof(double), (size_t)free_slot * 576 * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  memcpy(t->slot[free_slot].ke, ke, sizeof(t->slot[free_slot].ke));
+  t->slot[free_slot].refs = 1;
+  return free_slot;
+}
+void ebe_slot_release(int device, int slot) {
+  if (slot < 0 || slot >= kEbeMaxSlots) return;
+  std::lock_guard<std::mutex> lock(g_ebe_slot_mutex);
+  EbeSlotTable *t = ebe_slot_table(device);
+  if (t && t->slot[slot].refs > 0) t->slot[slot].refs -= 1;
+}
+}  // namespace
 
 extern "C" {
 
@@ -108,14 +166,41 @@ int pcgb_spmv(pcgb_csr_t A, const double *d_x, double *d_y, void *stream) {
   return spmv_launch(A->P, d_x, d_y, false, (cudaStream_t)stream);
 }
 
+static int csr_diag_compute(const CsrPlan &P, double *d_diag, cudaStream_t st) {
+  if (P.nrows == 0) return PCGB_OK;
+  if (!P.col) return fail(PCGB_ERR_ARG, "pcgb_csr_diag: the column array was released and no diagonal is cached");
+  const unsigned grid = (unsigned)((P.nrows * 8 + 255) / 256);
+  if (P.rp64) k_csr_diag<int64_t><<<grid, 256, 0, st>>>((const int64_t *)P.rowptr, P.col, P.val, P.nrows, d_diag);
+  else k_csr_diag<int32_t><<<grid, 256, 0, st>>>((const int32_t *)P.rowptr, P.col, P.val, P.nrows, d_diag);
+  PCGB_CHECK_LAUNCH();
+  return PCGB_OK;
+}
+
 int pcgb_csr_diag(pcgb_csr_t A, double *d_diag, void *stream) {
   if (!A || !d_diag) return fail(PCGB_ERR_ARG, "pcgb_csr_diag: null argument");
   const CsrPlan &P = A->P;
-  if (P.nrows == 0) return PCGB_OK;
-  const unsigned grid = (unsigned)((P.nrows * 8 + 255) / 256);
-  if (P.rp64) k_csr_diag<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int64_t *)P.rowptr, P.col, P.val, P.nrows, d_diag);
-  else k_csr_diag<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int32_t *)P.rowptr, P.col, P.val, P.nrows, d_diag);
-  PCGB_CHECK_LAUNCH();
+  if (P.diag_cache) {
+    PCGB_CUDA(cudaMemcpyAsync(d_diag, P.diag_cache, (size_t)P.nrows * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PCGB_OK;
+  }
+  return csr_diag_compute(P, d_diag, (cudaStream_t)stream);
+}
+
+/* The selected SpMV kernel may not read d_col at all (the persistent staged-x kernel works on its own 16-bit index
+ * stream).  pcgb_csr_release_col caches the diagonal (the one other consumer) and drops the library's reference, after
+ * which the caller may free d_col (2 GB at 128^3, 16 GB at 256^3).  Returns PCGB_ERR_ARG if the plan still needs it. */
+int pcgb_csr_release_col(pcgb_csr_t A, void *stream) {
+  if (!A) return fail(PCGB_ERR_ARG, "pcgb_csr_release_col: null argument");
+  CsrPlan &P = A->P;
+  if (!P.col) return PCGB_OK;
+  if (!P.persist) return fail(PCGB_ERR_ARG, "pcgb_csr_release_col: the selected SpMV kernel reads the column array");
+  if (!P.diag_cache && P.nrows > 0) {
+    PCGB_CUDA(cudaMalloc(&P.diag_cache, (size_t)P.nrows * sizeof(double)));
+    int rc = csr_diag_compute(P, P.diag_cache, (cudaStream_t)stream);
+    if (rc == PCGB_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(PCGB_ERR_CUDA, "pcgb_csr_release_col: sync failed");
+    if (rc != PCGB_OK) { cudaFree(P.diag_cache); P.diag_cache = nullptr; return rc; }
+  }
+  P.col = nullptr;
   return PCGB_OK;
 }
 
@@ -125,21 +210,47 @@ int64_t pcgb_spmv_bytes(pcgb_csr_t A) {
   return 12 * P.nnz + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows;
 }
 
-/* bytes the selected kernel actually streams from HBM per SpMV (staged-x: 10 B per non-zero + window tables) */
+/* bytes the selected kernel actually streams from HBM per SpMV: values 8 B per non-zero + the index stream
+ * (4 B columns for the L1-gather kernel, 2 B staged positions, or 2/3 B with the column-triple index) + row offsets,
+ * x, y and the tile / window tables */
 int64_t pcgb_spmv_stream_bytes(pcgb_csr_t A) {
   if (!A) return 0;
   const CsrPlan &P = A->P;
-  const int64_t per = P.staged ? 10 : 12;
-  return per * P.nnz + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows + (P.staged ? 8 * P.nwin + 8 * (int64_t)P.ntiles : 0) + 12 * (int64_t)P.ntiles;
+  const int64_t idx_bytes = (P.persist && P.t3) ? (2 * P.nnz) / 3 : (P.staged ? 2 * P.nnz : 4 * P.nnz);
+  return 8 * P.nnz + idx_bytes + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows +
+         (P.staged ? 8 * P.nwin + 8 * (int64_t)P.ntiles : 0) + (P.persist ? 32 : 12) * (int64_t)P.ntiles;
 }
 
-int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[12]) {
+int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[16]) {
   if (!A || !info) return fail(PCGB_ERR_ARG, "pcgb_csr_plan_info: null argument");
   const CsrPlan &P = A->P;
   info[0] = P.ntiles; info[1] = P.tile_items; info[2] = P.lanes; info[3] = P.snap ? 1 : 0;
   info[4] = P.nfix; info[5] = P.staged ? P.smem_staged : P.smem_bytes; info[6] = P.max_row; info[7] = P.use_tma ? 1 : 0;
   info[8] = P.persist ? 2 : (P.staged ? 1 : 0); info[9] = P.nwin; info[10] = P.cap_x; info[11] = P.max_nw;
   if (P.persist) info[5] = P.smem_persist;
+  info[12] = P.t3 ? 1 : 0; info[13] = P.desc_split ? P.nb_tiles : -1; info[14] = P.persist ? P.grid_persist : 0; info[15] = P.col ? 0 : 1;
+  return PCGB_OK;
+}
+
+/* Interface-first split of the SpMV (multi-GPU overlap, SURVEY 8(e) "order boundary rows first, launch exchange, compute
+ * interior rows"): d_rows = the distinct local rows that take part in the interface exchange.  The solver registers
+ * them itself from its halo plan; the two entry points below exist so that the split can be tested on one GPU. */
+int pcgb_csr_set_boundary_rows(pcgb_csr_t A, const int32_t *d_rows, int64_t count, void *stream) {
+  if (!A || count < 0 || (count > 0 && !d_rows)) return fail(PCGB_ERR_ARG, "pcgb_csr_set_boundary_rows: bad argument");
+  return spmv_set_boundary_rows(A->P, d_rows, count, (cudaStream_t)stream);
+}
+/* y = A x as two launches (interface tiles, then the rest); out_dot (device, may be NULL) receives x.y */
+int pcgb_spmv_split(pcgb_csr_t A, const double *d_x, double *d_y, double *d_out_dot, void *stream) {
+  if (!A || !d_x || !d_y) return fail(PCGB_ERR_ARG, "pcgb_spmv_split: null argument");
+  const CsrPlan &P = A->P;
+  if (!spmv_split_available(P)) return fail(PCGB_ERR_ARG, "pcgb_spmv_split: no split plan (persistent kernel + registered boundary rows needed)");
+  cudaStream_t st = (cudaStream_t)stream;
+  PCGB_TRY(spmv_launch_part(P, 0, d_x, d_y, d_out_dot != nullptr, st));
+  PCGB_TRY(spmv_launch_part(P, 1, d_x, d_y, d_out_dot != nullptr, st));
+  if (d_out_dot) {
+    k_reduce<1, 0><<<1, 256, 0, st>>>(nullptr, P.dot_partials_split, spmv_split_dot_count(P), 0, d_out_dot, nullptr);
+    PCGB_CHECK_LAUNCH();
+  }
   return PCGB_OK;
 }
 
@@ -158,12 +269,14 @@ int pcgb_dot_w(int64_t n, const double *d_a, const double *d_b, const double *d_
   if (n < 0 || !d_out || (n > 0 && (!d_a || !d_b))) return fail(PCGB_ERR_ARG, "pcgb_dot_w: bad argument");
   PCGB_TRY(require_device());
   cudaStream_t st = (cudaStream_t)stream;
-  static thread_local double *scratch = nullptr;
-  if (!scratch) PCGB_CUDA(cudaMalloc(&scratch, kMaxVecGrid * sizeof(double)));
+  // stream-ordered scratch on the CURRENT device: no state shared between calls, streams or devices
+  double *scratch = nullptr;
+  PCGB_CUDA(cudaMallocAsync(&scratch, kMaxVecGrid * sizeof(double), st));
   const int grid = vec_grid(n);
   k_dot_w<<<grid, kVecBlock, 0, st>>>(n, d_a, d_b, d_w, scratch);
-  PCGB_CHECK_LAUNCH();
-  return reduce_rows(scratch, grid, 1, d_out, st);
+  int rc = cudaGetLastError() == cudaSuccess ? reduce_rows(scratch, grid, 1, d_out, st) : fail(PCGB_ERR_CUDA, "pcgb_dot_w: launch failed");
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 int pcgb_axpby(int64_t n, double a, const double *d_x, double b, double *d_y, void *stream) {
@@ -201,38 +314,105 @@ int pcgb_comm_unique_id(unsigned char id[PCGB_UNIQUE_ID_BYTES]) {
   return PCGB_OK;
 }
 
-int pcgb_comm_create(int rank, int nranks, const unsigned char id[PCGB_UNIQUE_ID_BYTES], pcgb_comm_t *out) {
-  if (!out || !id || rank < 0 || rank >= nranks) return fail(PCGB_ERR_ARG, "pcgb_comm_create: bad argument");
+int pcgb_comm_create(int rank, int nranks, const unsigned char *id, pcgb_comm_t *out) {
+  if (!out || rank < 0 || rank >= nranks) return fail(PCGB_ERR_ARG, "pcgb_comm_create: bad argument");
+  if (!id && nranks > kMaxPeers) return fail(PCGB_ERR_ARG, "pcgb_comm_create: a peer-only communicator holds at most %d ranks", kMaxPeers);
   PCGB_TRY(require_device());
-  NcclApi *api = nullptr;
-  PCGB_TRY(nccl_api(&api));
-  ncclUniqueId uid;
-  memcpy(&uid, id, sizeof(uid));
   pcgb_comm_t c = new pcgb_comm_s();
-  c->api = api; c->rank = rank; c->nranks = nranks;
-  int e = api->CommInitRank(&c->comm, nranks, uid, rank);
-  if (e != ncclSuccess) {
-    delete c;
-    return fail(PCGB_ERR_NCCL, "ncclCommInitRank -> %s", api->GetErrorString ? api->GetErrorString(e) : "error");
+  c->rank = rank; c->nranks = nranks;
+  cudaGetDevice(&c->device);
+  int rc = PCGB_OK;
+  if (id) {
+    NcclApi *api = nullptr;
+    rc = nccl_api(&api);
+    if (rc == PCGB_OK) {
+      ncclUniqueId uid;
+      memcpy(&uid, id, sizeof(uid));
+      c->api = api;
+      int e = api->CommInitRank(&c->comm, nranks, uid, rank);
+      if (e != ncclSuccess) rc = fail(PCGB_ERR_NCCL, "ncclCommInitRank -> %s", api->GetErrorString ? api->GetErrorString(e) : "error");
+    }
   }
+  // the peer window: zeroed before anyone can import it
+  cudaError_t ce = cudaSuccess;
+  if (rc == PCGB_OK && nranks <= kMaxPeers) {
+    if ((ce = cudaMalloc(&c->win, kWinBytes)) == cudaSuccess && (ce = cudaMemset(c->win, 0, kWinBytes)) == cudaSuccess &&
+        (ce = cudaMalloc(&c->d_status, sizeof(int))) == cudaSuccess && (ce = cudaMemset(c->d_status, 0, sizeof(int))) == cudaSuccess &&
+        (ce = cudaMallocHost(&c->h_status, sizeof(int))) == cudaSuccess)
+      ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) rc = fail(PCGB_ERR_CUDA, "pcgb_comm_create: window allocation -> %s", cudaGetErrorString(ce));
+  }
+  const char *tr = getenv("PCGB_COMM");
+  c->transport = (tr && (tr[0] == 'n' || tr[0] == 'N')) ? PCGB_TRANSPORT_NCCL : PCGB_TRANSPORT_PEER;
+  if (rc != PCGB_OK) { pcgb_comm_destroy(c); return rc; }
   *out = c;
   return PCGB_OK;
 }
 
 int pcgb_comm_destroy(pcgb_comm_t c) {
   if (!c) return PCGB_OK;
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  cudaFree(c->win); cudaFree(c->d_status);
+  if (c->h_status) cudaFreeHost(c->h_status);
   if (c->comm && c->api && c->api->CommDestroy) c->api->CommDestroy(c->comm);
   delete c;
   return PCGB_OK;
 }
 
-int pcgb_allreduce_sum(pcgb_comm_t c, double *d_buf, int count, void *stream) {
-  if (!c || !d_buf || count < 0) return fail(PCGB_ERR_ARG, "pcgb_allreduce_sum: bad argument");
-  PCGB_NCCL(c->api, c->api->AllReduce(d_buf, d_buf, (size_t)count, ncclFloat64, ncclSum, c->comm, (cudaStream_t)stream));
+/* Peer windows: every rank exports the CUDA IPC handle of its window, the host code all-gathers the blobs over ANY
+ * side channel (torch.distributed object collectives, mpi4py allgather, ...) and every rank imports them.  From then
+ * on the all-reduces and the halo exchange of this communicator are the library's own kernels over NVLink peer memory
+ * (csrc/peer.cuh) unless PCGB_COMM=nccl / pcgb_comm_set_transport(c, 0) keeps NCCL. */
+int pcgb_comm_window_export(pcgb_comm_t c, unsigned char blob[PCGB_IPC_BLOB_BYTES]) {
+  if (!c || !blob) return fail(PCGB_ERR_ARG, "pcgb_comm_window_export: null argument");
+  if (!c->win) return fail(PCGB_ERR_ARG, "pcgb_comm_window_export: communicator has no window (more than %d ranks)", kMaxPeers);
+  static_assert(sizeof(cudaIpcMemHandle_t) == PCGB_IPC_BLOB_BYTES, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t h;
+  PCGB_CUDA(cudaIpcGetMemHandle(&h, c->win));
+  memcpy(blob, &h, sizeof(h));
   return PCGB_OK;
 }
 
+int pcgb_comm_window_import(pcgb_comm_t c, const unsigned char *blobs) {
+  if (!c || !blobs) return fail(PCGB_ERR_ARG, "pcgb_comm_window_import: null argument");
+  if (!c->win) return fail(PCGB_ERR_ARG, "pcgb_comm_window_import: communicator has no window");
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank || c->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, blobs + (size_t)r * PCGB_IPC_BLOB_BYTES, sizeof(h));
+    void *ptr = nullptr;
+    PCGB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[r] = static_cast<unsigned long long *>(ptr);
+  }
+  c->peer_ready = true;
+  return PCGB_OK;
+}
+
+int pcgb_comm_transport(pcgb_comm_t c) { return c && c->use_peer() ? PCGB_TRANSPORT_PEER : PCGB_TRANSPORT_NCCL; }
+int pcgb_comm_set_transport(pcgb_comm_t c, int transport) {
+  if (!c || (transport != PCGB_TRANSPORT_NCCL && transport != PCGB_TRANSPORT_PEER)) return fail(PCGB_ERR_ARG, "pcgb_comm_set_transport: bad argument");
+  if (transport == PCGB_TRANSPORT_PEER && !c->peer_ready) return fail(PCGB_ERR_ARG, "pcgb_comm_set_transport: peer windows have not been imported");
+  if (transport == PCGB_TRANSPORT_NCCL && !c->api) return fail(PCGB_ERR_ARG, "pcgb_comm_set_transport: communicator was created without NCCL");
+  c->transport = transport;
+  return PCGB_OK;
+}
+/* 0 = healthy; non-zero after a peer kernel gave up waiting for another rank (sticky) */
+int pcgb_comm_status(pcgb_comm_t c, void *stream) {
+  if (!c || !c->d_status) return 0;
+  if (cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+    return -1;
+  return *c->h_status;
+}
+
+int pcgb_allreduce_sum(pcgb_comm_t c, double *d_buf, int count, void *stream) {
+  if (!c || !d_buf || count < 0) return fail(PCGB_ERR_ARG, "pcgb_allreduce_sum: bad argument");
+  return allreduce_sum(c, d_buf, count, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------ halo plan
+
 int pcgb_halo_create(pcgb_comm_t c, int n_nbr, const int32_t *nbr_rank, const int64_t *nbr_ptr, const int64_t *idx_host,
                      int64_t nlocal, pcgb_halo_t *out) {
   if (!out || n_nbr < 0 || (n_nbr > 0 && (!c || !nbr_rank || !nbr_ptr))) return fail(PCGB_ERR_ARG, "pcgb_halo_create: bad argument");
@@ -243,13 +423,23 @@ int pcgb_halo_create(pcgb_comm_t c, int n_nbr, const int32_t *nbr_rank, const in
   if (n_nbr > 0) h->nbr_ptr.assign(nbr_ptr, nbr_ptr + n_nbr + 1);
   else h->nbr_ptr.assign(1, 0);
   h->m = h->nbr_ptr.back();
-  if (h->m > INT32_MAX) { delete h; return fail(PCGB_ERR_ARG, "pcgb_halo_create: too many shared dofs"); }
-  if (h->m > 0) {
-    std::vector<int> idx((size_t)h->m);
-    for (int64_t k = 0; k < h->m; ++k) {
-      if (idx_host[k] < 0 || idx_host[k] >= nlocal) { delete h; return fail(PCGB_ERR_ARG, "pcgb_halo_create: index %lld out of range", (long long)idx_host[k]); }
-      idx[(size_t)k] = (int)idx_host[k];
+  int rc = PCGB_OK;
+  cudaError_t ce = cudaSuccess;
+  if (h->m > INT32_MAX) rc = fail(PCGB_ERR_ARG, "pcgb_halo_create: too many shared dofs");
+  for (int j = 0; j < n_nbr && rc == PCGB_OK; ++j)
+    if (nbr_rank[j] < 0 || nbr_rank[j] >= c->nranks || nbr_rank[j] == c->rank || nbr_ptr[j + 1] < nbr_ptr[j])
+      rc = fail(PCGB_ERR_ARG, "pcgb_halo_create: bad neighbour table at slot %d", j);
+  std::vector<int> idx((size_t)h->m), ent_nbr((size_t)h->m), nptr((size_t)n_nbr + 1);
+  if (rc == PCGB_OK && h->m > 0) {
+    for (int j = 0; j < n_nbr; ++j)
+      for (int64_t k = nbr_ptr[j]; k < nbr_ptr[j + 1]; ++k) ent_nbr[(size_t)k] = j;
+    for (int64_t k = 0; k < h->m && rc == PCGB_OK; ++k) {
+      if (idx_host[k] < 0 || idx_host[k] >= nlocal) rc = fail(PCGB_ERR_ARG, "pcgb_halo_create: index %lld out of range", (long long)idx_host[k]);
+      else idx[(size_t)k] = (int)idx_host[k];
     }
+  }
+  if (rc == PCGB_OK) {
+    for (int j = 0; j <= n_nbr; ++j) nptr[(size_t)j] = (int)h->nbr_ptr[(size_t)j];
     // group the receive positions by dof, neighbour order inside a dof (stable: k ascending = neighbour ascending)
     std::vector<int> order((size_t)h->m);
     for (int64_t k = 0; k < h->m; ++k) order[(size_t)k] = (int)k;
@@ -262,26 +452,87 @@ int pcgb_halo_create(pcgb_comm_t c, int n_nbr, const int32_t *nbr_rank, const in
     }
     ptr.push_back((int)h->m);
     h->ndof = (int64_t)dof.size();
-    auto up = [&](int **d, const std::vector<int> &v) -> cudaError_t {
-      cudaError_t e = cudaMalloc(d, v.size() * sizeof(int));
-      if (e != cudaSuccess) return e;
-      return cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
-    };
-    PCGB_CUDA(up(&h->d_idx, idx));
-    PCGB_CUDA(up(&h->d_dof, dof));
-    PCGB_CUDA(up(&h->d_ptr, ptr));
-    PCGB_CUDA(up(&h->d_pos, pos));
-    PCGB_CUDA(cudaMalloc(&h->d_send, (size_t)h->m * sizeof(double)));
-    PCGB_CUDA(cudaMalloc(&h->d_recv, (size_t)h->m * sizeof(double)));
+    // receive block shared with the neighbours: [2][m] doubles + [n_nbr][2] flags (peer transport)
+    h->blk_bytes = (size_t)2 * (size_t)h->m * sizeof(double) + (size_t)2 * (size_t)std::max(n_nbr, 1) * sizeof(unsigned long long);
+    if ((ce = upload(&h->d_idx, idx)) == cudaSuccess && (ce = upload(&h->d_dof, dof)) == cudaSuccess &&
+        (ce = upload(&h->d_ptr, ptr)) == cudaSuccess && (ce = upload(&h->d_pos, pos)) == cudaSuccess &&
+        (ce = upload(&h->d_nbr_ptr, nptr)) == cudaSuccess && (ce = upload(&h->d_ent_nbr, ent_nbr)) == cudaSuccess &&
+        (ce = cudaMalloc(&h->d_send, std::max<size_t>((size_t)h->m, 1) * sizeof(double))) == cudaSuccess &&
+        (ce = cudaMalloc(&h->d_recv, std::max<size_t>((size_t)h->m, 1) * sizeof(double))) == cudaSuccess &&
+        (ce = cudaMalloc(&h->blk, h->blk_bytes)) == cudaSuccess && (ce = cudaMemset(h->blk, 0, h->blk_bytes)) == cudaSuccess &&
+        (ce = cudaMalloc(&h->d_epoch, 2 * sizeof(unsigned long long))) == cudaSuccess &&
+        (ce = cudaMemset(h->d_epoch, 0, 2 * sizeof(unsigned long long))) == cudaSuccess)
+      ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) rc = fail(PCGB_ERR_CUDA, "pcgb_halo_create: %s", cudaGetErrorString(ce));
   }
+  if (rc != PCGB_OK) { pcgb_halo_destroy(h); return rc; }
   *out = h;
   return PCGB_OK;
 }
 
 int pcgb_halo_destroy(pcgb_halo_t h) {
   if (!h) return PCGB_OK;
+  for (void *p : h->opened) cudaIpcCloseMemHandle(p);
   cudaFree(h->d_idx); cudaFree(h->d_dof); cudaFree(h->d_ptr); cudaFree(h->d_pos); cudaFree(h->d_send); cudaFree(h->d_recv);
+  cudaFree(h->blk); cudaFree(h->d_nbr_ptr); cudaFree(h->d_ent_nbr); cudaFree(h->d_remote); cudaFree(h->d_remote_m);
+  cudaFree(h->d_remote_flag); cudaFree(h->d_epoch);
   delete h;
+  return PCGB_OK;
+}
+
+/* Peer transport of the halo: export / all-gather (host side channel) / import, like the communicator window.
+ * Every rank of the communicator takes part, also one without neighbours. */
+int64_t pcgb_halo_blob_bytes(pcgb_halo_t h) {
+  if (!h || !h->comm) return 0;
+  return (int64_t)(sizeof(HaloBlobHead) + (size_t)h->comm->nranks * sizeof(HaloBlobRank));
+}
+
+int pcgb_halo_export(pcgb_halo_t h, unsigned char *blob) {
+  if (!h || !blob || !h->comm) return fail(PCGB_ERR_ARG, "pcgb_halo_export: null argument");
+  HaloBlobHead head;
+  memset(&head, 0, sizeof(head));
+  cudaIpcMemHandle_t ih;
+  PCGB_CUDA(cudaIpcGetMemHandle(&ih, h->blk));
+  memcpy(head.handle, &ih, sizeof(ih));
+  head.m = h->m;
+  memcpy(blob, &head, sizeof(head));
+  std::vector<HaloBlobRank> tab((size_t)h->comm->nranks, HaloBlobRank{-1, -1, 0});
+  for (int j = 0; j < h->n_nbr; ++j) tab[(size_t)h->nbr_rank[j]] = HaloBlobRank{h->nbr_ptr[j], j, h->nbr_ptr[j + 1] - h->nbr_ptr[j]};
+  memcpy(blob + sizeof(head), tab.data(), tab.size() * sizeof(HaloBlobRank));
+  return PCGB_OK;
+}
+
+int pcgb_halo_import(pcgb_halo_t h, const unsigned char *blobs) {
+  if (!h || !blobs || !h->comm) return fail(PCGB_ERR_ARG, "pcgb_halo_import: null argument");
+  if (h->peer_ready) return PCGB_OK;
+  const size_t stride = (size_t)pcgb_halo_blob_bytes(h);
+  const int me = h->comm->rank;
+  std::vector<double *> remote((size_t)h->n_nbr, nullptr);
+  std::vector<int64_t> remote_m((size_t)h->n_nbr, 0);
+  std::vector<unsigned long long *> remote_flag((size_t)h->n_nbr, nullptr);
+  for (int j = 0; j < h->n_nbr; ++j) {
+    const unsigned char *b = blobs + (size_t)h->nbr_rank[j] * stride;
+    HaloBlobHead head;
+    HaloBlobRank mine;
+    memcpy(&head, b, sizeof(head));
+    memcpy(&mine, b + sizeof(head) + (size_t)me * sizeof(HaloBlobRank), sizeof(mine));
+    const int64_t cnt = h->nbr_ptr[j + 1] - h->nbr_ptr[j];
+    if (mine.off < 0 || mine.cnt != cnt)
+      return fail(PCGB_ERR_ARG, "pcgb_halo_import: rank %d shares %lld dofs with rank %d but that rank lists %lld for us (interface lists must match)",
+                  me, (long long)cnt, h->nbr_rank[j], (long long)mine.cnt);
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, head.handle, sizeof(ih));
+    void *ptr = nullptr;
+    PCGB_CUDA(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->opened.push_back(ptr);
+    remote[(size_t)j] = static_cast<double *>(ptr) + mine.off;
+    remote_m[(size_t)j] = head.m;
+    remote_flag[(size_t)j] = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ptr) + (size_t)2 * (size_t)head.m * sizeof(double)) + 2 * mine.slot;
+  }
+  PCGB_CUDA(upload(&h->d_remote, remote));
+  PCGB_CUDA(upload(&h->d_remote_m, remote_m));
+  PCGB_CUDA(upload(&h->d_remote_flag, remote_flag));
+  h->peer_ready = true;
   return PCGB_OK;
 }
 
@@ -298,51 +549,53 @@ int pcgb_ebe_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, pcgb_e
   if (n >= (1 << 30)) return fail(PCGB_ERR_ARG, "pcgb_ebe_create: more than 2^30 dofs");
   PCGB_TRY(require_device());
   pcgb_ebe_t E = new pcgb_ebe_s();
+  cudaGetDevice(&E->device);
   EbePlan &P = E->P;
   P.n = n;
-  int slots = 0;
   std::vector<int> blk_group;
   std::vector<int64_t> blk_e0;
   P.bytes = 16 * n;
-  for (int g = 0; g < ngroups; ++g) {
+  int rc = PCGB_OK;
+  cudaError_t ce = cudaSuccess;
+  for (int g = 0; g < ngroups && rc == PCGB_OK; ++g) {
     const pcgb_ebe_group &src = groups[g];
     if (src.nd <= 0 || src.nd > 96 || src.ne < 0 || !src.ke_host || (src.ne > 0 && (!src.d_idx || !src.d_ck))) {
-      delete E;
-      return fail(PCGB_ERR_ARG, "pcgb_ebe_create: group %d: pattern size must be 1..96 and arrays non-null", g);
+      rc = fail(PCGB_ERR_ARG, "pcgb_ebe_create: group %d: pattern size must be 1..96 and arrays non-null", g);
+      break;
     }
     EbeGroup eg;
     eg.nd = src.nd; eg.ne = src.ne; eg.idx = src.d_idx; eg.sign = src.d_sign; eg.ck = src.d_ck;
     double *dke = nullptr;
-    PCGB_CUDA(cudaMalloc(&dke, (size_t)src.nd * src.nd * sizeof(double)));
-    PCGB_CUDA(cudaMemcpy(dke, src.ke_host, (size_t)src.nd * src.nd * sizeof(double), cudaMemcpyHostToDevice));
-    eg.ke = dke;
-    if (src.nd == 24 && slots < kEbeMaxSlots) {
-      PCGB_CUDA(cudaMemcpyToSymbol(c_ebe_ke24, src.ke_host, 576 * sizeof(double), (size_t)slots * 576 * sizeof(double)));
-      eg.slot = slots++;
-    } else {
-      for (int64_t e0 = 0; e0 < src.ne; e0 += kEbeWarpsPerBlock) { blk_group.push_back((int)P.groups.size()); blk_e0.push_back(e0); }
+    if ((ce = cudaMalloc(&dke, (size_t)src.nd * src.nd * sizeof(double))) != cudaSuccess ||
+        (ce = cudaMemcpy(dke, src.ke_host, (size_t)src.nd * src.nd * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(dke);
+      rc = fail(PCGB_ERR_CUDA, "pcgb_ebe_create: %s", cudaGetErrorString(ce));
+      break;
     }
+    eg.ke = dke;
+    if (src.nd == 24) eg.slot = ebe_slot_acquire(src.ke_host);
+    if (eg.slot < 0)
+      for (int64_t e0 = 0; e0 < src.ne; e0 += kEbeWarpsPerBlock) { blk_group.push_back((int)P.groups.size()); blk_e0.push_back(e0); }
     P.bytes += src.ne * ((int64_t)src.nd * (4 + (src.d_sign ? 1 : 0)) + 8);
     P.groups.push_back(eg);
   }
-  if (!P.groups.empty()) {
-    PCGB_CUDA(cudaMalloc(&P.d_groups, P.groups.size() * sizeof(EbeGroup)));
-    PCGB_CUDA(cudaMemcpy(P.d_groups, P.groups.data(), P.groups.size() * sizeof(EbeGroup), cudaMemcpyHostToDevice));
+  if (rc == PCGB_OK) {
+    P.nblk_warp = (int)blk_group.size();
+    if ((ce = upload(&P.d_groups, P.groups)) != cudaSuccess || (ce = upload(&P.d_blk_group, blk_group)) != cudaSuccess ||
+        (ce = upload(&P.d_blk_e0, blk_e0)) != cudaSuccess)
+      rc = fail(PCGB_ERR_CUDA, "pcgb_ebe_create: %s", cudaGetErrorString(ce));
   }
-  P.nblk_warp = (int)blk_group.size();
-  if (P.nblk_warp > 0) {
-    PCGB_CUDA(cudaMalloc(&P.d_blk_group, blk_group.size() * sizeof(int)));
-    PCGB_CUDA(cudaMalloc(&P.d_blk_e0, blk_e0.size() * sizeof(int64_t)));
-    PCGB_CUDA(cudaMemcpy(P.d_blk_group, blk_group.data(), blk_group.size() * sizeof(int), cudaMemcpyHostToDevice));
-    PCGB_CUDA(cudaMemcpy(P.d_blk_e0, blk_e0.data(), blk_e0.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-  }
+  if (rc != PCGB_OK) { pcgb_ebe_destroy(E); return rc; }
   *out = E;
   return PCGB_OK;
 }
 
 int pcgb_ebe_destroy(pcgb_ebe_t E) {
   if (!E) return PCGB_OK;
-  for (EbeGroup &g : E->P.groups) cudaFree(const_cast<double *>(g.ke));
+  for (EbeGroup &g : E->P.groups) {
+    cudaFree(const_cast<double *>(g.ke));
+    ebe_slot_release(E->device, g.slot);
+  }
   cudaFree(E->P.d_groups); cudaFree(E->P.d_blk_group); cudaFree(E->P.d_blk_e0);
   delete E;
   return PCGB_OK;
@@ -365,10 +618,10 @@ int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const
   for (int g = 1; g < ngroups; ++g)
     if (phase[g] < phase[g - 1]) return fail(PCGB_ERR_ARG, "pcgb_ebe2_create: groups must be sorted by phase (colour)");
   pcgb_ebe2_t E = new pcgb_ebe2_s();
+  cudaGetDevice(&E->device);
   EbePlan &P = E->C.P;
   P.n = n;
   P.bytes = 16 * n;
-  std::vector<const double *> slot_key;
   std::vector<int> blk_group;
   std::vector<int64_t> blk_e0;
   std::vector<std::pair<const double *, double *>> ke_dev;   // host pointer -> device copy (shared between colours)
@@ -395,13 +648,7 @@ int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const
     eg.ke = dke;
     bool t24 = false;
     if (src.nd == 24) {
-      int slot = -1;
-      for (size_t k = 0; k < slot_key.size(); ++k) if (slot_key[k] == src.ke_host) slot = (int)k;
-      if (slot < 0 && (int)slot_key.size() < kEbeMaxSlots) {
-        slot = (int)slot_key.size();
-        PCGB_CUDA(cudaMemcpyToSymbol(c_ebe_ke24, src.ke_host, 576 * sizeof(double), (size_t)slot * 576 * sizeof(double)));
-        slot_key.push_back(src.ke_host);
-      }
+      const int slot = ebe_slot_acquire(src.ke_host);   // shared per-device table: never overwrites a live operator's matrices
       if (slot >= 0) { eg.slot = slot; t24 = true; }
     }
     if (t24) {
@@ -441,6 +688,7 @@ int pcgb_ebe2_destroy(pcgb_ebe2_t E) {
     bool done = false;
     for (const double *f : freed) done |= (f == g.ke);
     if (!done) { cudaFree(const_cast<double *>(g.ke)); freed.push_back(g.ke); }
+    ebe_slot_release(E->device, g.slot);
   }
   cudaFree(E->C.P.d_groups); cudaFree(E->C.P.d_blk_group); cudaFree(E->C.P.d_blk_e0);
   delete E;
@@ -461,25 +709,28 @@ static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pc
   pcgb_solver_t s = new pcgb_solver_s();
   s->A = A; s->E = E; s->halo = halo; s->comm = comm; s->n = A ? A->P.nrows : E->P.n;
   const size_t nb = (size_t)(s->n > 0 ? s->n : 1) * sizeof(double);
-  PCGB_CUDA(cudaMalloc(&s->r, nb));
-  PCGB_CUDA(cudaMalloc(&s->p, nb));
-  PCGB_CUDA(cudaMalloc(&s->q, nb));
-  PCGB_CUDA(cudaMalloc(&s->xalt, nb));
-  PCGB_CUDA(cudaMalloc(&s->xown, nb));
-  PCGB_CUDA(cudaMemset(s->p, 0, nb));
-  PCGB_CUDA(cudaMalloc(&s->partials, 5 * kMaxVecGrid * sizeof(double)));
   s->stage_cap = ((A ? A->P.ntiles : 0) + 4095) / 4096 + 1;
-  PCGB_CUDA(cudaMalloc(&s->stage, (size_t)s->stage_cap * sizeof(double)));
-  PCGB_CUDA(cudaMalloc(&s->red, 8 * sizeof(double)));
-  PCGB_CUDA(cudaMemset(s->red, 0, 8 * sizeof(double)));
-  PCGB_CUDA(cudaMalloc(&s->d_ctrl, sizeof(PcgCtrl)));
-  PCGB_CUDA(cudaMallocHost(&s->h_ctrl, sizeof(PcgCtrl)));
-  PCGB_CUDA(cudaMallocHost(&s->h_red, 8 * sizeof(double)));
-  PCGB_CUDA(cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking));
-  PCGB_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
-  PCGB_CUDA(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
-  PCGB_CUDA(cudaEventCreate(&s->ev_l0));
-  PCGB_CUDA(cudaEventCreate(&s->ev_l1));
+  cudaError_t ce = cudaSuccess;
+  int rc = PCGB_OK;
+  if ((ce = cudaMalloc(&s->r, nb)) == cudaSuccess && (ce = cudaMalloc(&s->p, nb)) == cudaSuccess &&
+      (ce = cudaMalloc(&s->q, nb)) == cudaSuccess && (ce = cudaMalloc(&s->xalt, nb)) == cudaSuccess &&
+      (ce = cudaMalloc(&s->xown, nb)) == cudaSuccess && (ce = cudaMemset(s->p, 0, nb)) == cudaSuccess &&
+      (ce = cudaMalloc(&s->partials, 5 * kMaxVecGrid * sizeof(double))) == cudaSuccess &&
+      (ce = cudaMalloc(&s->stage, (size_t)s->stage_cap * sizeof(double))) == cudaSuccess &&
+      (ce = cudaMalloc(&s->red, 8 * sizeof(double))) == cudaSuccess && (ce = cudaMemset(s->red, 0, 8 * sizeof(double))) == cudaSuccess &&
+      (ce = cudaMalloc(&s->d_ctrl, sizeof(PcgCtrl))) == cudaSuccess && (ce = cudaMallocHost(&s->h_ctrl, sizeof(PcgCtrl))) == cudaSuccess &&
+      (ce = cudaMallocHost(&s->h_red, 8 * sizeof(double))) == cudaSuccess &&
+      (ce = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking)) == cudaSuccess &&
+      (ce = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming)) == cudaSuccess &&
+      (ce = cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming)) == cudaSuccess &&
+      (ce = cudaEventCreate(&s->ev_l0)) == cudaSuccess && (ce = cudaEventCreate(&s->ev_l1)) == cudaSuccess &&
+      (ce = cudaEventCreate(&s->ev_s0)) == cudaSuccess)
+    ce = cudaEventCreate(&s->ev_s1);
+  if (ce != cudaSuccess) rc = fail(PCGB_ERR_CUDA, "pcgb_solver_create: %s", cudaGetErrorString(ce));
+  // interface-first tile order: the tiles owning exchanged rows run first, their values travel while the rest computes
+  if (rc == PCGB_OK && A && halo && halo->ndof > 0 && env_int("PCGB_OVERLAP", 1) != 0)
+    rc = spmv_set_boundary_rows(A->P, halo->d_dof, halo->ndof, s->own);
+  if (rc != PCGB_OK) { pcgb_solver_destroy(s); return rc; }
   *out = s;
   return PCGB_OK;
 }
@@ -503,10 +754,13 @@ int pcgb_solver_destroy(pcgb_solver_t s) {
   if (s->ev_out) cudaEventDestroy(s->ev_out);
   if (s->ev_l0) cudaEventDestroy(s->ev_l0);
   if (s->ev_l1) cudaEventDestroy(s->ev_l1);
+  if (s->ev_s0) cudaEventDestroy(s->ev_s0);
+  if (s->ev_s1) cudaEventDestroy(s->ev_s1);
   for (cudaEvent_t e : s->ev_k) cudaEventDestroy(e);
   cudaFree(s->r); cudaFree(s->p); cudaFree(s->q); cudaFree(s->xalt); cudaFree(s->xown); cudaFree(s->partials); cudaFree(s->stage);
   cudaFree(s->red); cudaFree(s->d_ctrl);
-  cudaFreeHost(s->h_ctrl); cudaFreeHost(s->h_red);
+  if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+  if (s->h_red) cudaFreeHost(s->h_red);
   delete s;
   return PCGB_OK;
 }
@@ -516,6 +770,9 @@ int pcgb_solver_destroy(pcgb_solver_t s) {
 // ---- host helpers of the solve -------------------------------------------------------------
 namespace {
 
+inline bool multi_rank(pcgb_solver_t s) { return s->comm && s->comm->nranks > 1; }
+inline bool peer_path(pcgb_solver_t s) { return multi_rank(s) && s->comm->use_peer() && (!s->halo || s->halo->m == 0 || s->halo->use_peer()); }
+
 // y = A x + interface sum  (calcMPFint, pcg_solver.py:339-342)
 int op_apply(pcgb_solver_t s, const double *x, double *y, cudaStream_t st) {
   if (s->E) PCGB_TRY(ebe_apply(s->E->P, x, y, st, &s->launches));
@@ -524,25 +781,38 @@ int op_apply(pcgb_solver_t s, const double *x, double *y, cudaStream_t st) {
   return PCGB_OK;
 }
 
-// sum `nv` rows of s->partials (count entries each) over blocks and ranks; result in s->h_red[0..nv)
-int reduce_to_host(pcgb_solver_t s, int count, int nv, cudaStream_t st) {
-  double *dst = s->red + 6;  // nv <= 2
-  PCGB_TRY(reduce_rows(s->partials, count, nv, dst, st));
+// sum `nv` (<= 2) rows of s->partials over blocks and ranks into the device scalars s->red[dst .. dst+nv)
+int reduce_to_device(pcgb_solver_t s, int count, int nv, int dst, cudaStream_t st) {
+  PCGB_TRY(reduce_rows(s->partials, count, nv, s->red + dst, st));
   s->launches += 1;
-  if (s->comm && s->comm->nranks > 1) PCGB_TRY(pcgb_allreduce_sum(s->comm, dst, nv, st));
-  PCGB_CUDA(cudaMemcpyAsync(s->h_red, dst, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (multi_rank(s)) {
+    PCGB_TRY(allreduce_sum(s->comm, s->red + dst, nv, st));
+    if (s->comm->use_peer()) s->launches += 1;
+  }
+  return PCGB_OK;
+}
+
+// q = A x ; r = b - q ; sum r*r*w over all ranks -> s->red[dst] (device)
+int true_residual_dev(pcgb_solver_t s, const double *b, const double *w, const double *x, int dst, cudaStream_t st) {
+  PCGB_TRY(op_apply(s, x, s->q, st));
+  const int grid = vec_grid(s->n);
+  k_residual<<<grid, kVecBlock, 0, st>>>(s->n, b, s->q, w, s->r, s->partials);
+  PCGB_CHECK_LAUNCH();
+  s->launches += 1;
+  return reduce_to_device(s, grid, 1, dst, st);
+}
+
+// host copy of s->red[6..8) (one synchronisation)
+int fetch_red(pcgb_solver_t s, cudaStream_t st) {
+  PCGB_CUDA(cudaMemcpyAsync(s->h_red, s->red + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   PCGB_CUDA(cudaStreamSynchronize(st));
   return PCGB_OK;
 }
 
 // r = b - A x ; returns sqrt(sum r*r*w) over all ranks
 int true_residual(pcgb_solver_t s, const double *b, const double *w, const double *x, double *normr, cudaStream_t st) {
-  PCGB_TRY(op_apply(s, x, s->q, st));
-  const int grid = vec_grid(s->n);
-  k_residual<<<grid, kVecBlock, 0, st>>>(s->n, b, s->q, w, s->r, s->partials);
-  PCGB_CHECK_LAUNCH();
-  s->launches += 1;
-  PCGB_TRY(reduce_to_host(s, grid, 1, st));
+  PCGB_TRY(true_residual_dev(s, b, w, x, 6, st));
+  PCGB_TRY(fetch_red(s, st));
   *normr = std::sqrt(s->h_red[0]);
   return PCGB_OK;
 }
@@ -552,18 +822,18 @@ int rz_to_device(pcgb_solver_t s, const double *minv, const double *w, cudaStrea
   const int grid = vec_grid(s->n);
   k_rz<<<grid, kVecBlock, 0, st>>>(s->n, s->r, minv, w, s->partials);
   PCGB_CHECK_LAUNCH();
-  PCGB_TRY(reduce_rows(s->partials, grid, 2, s->red + 6, st));
-  s->launches += 2;
-  if (s->comm && s->comm->nranks > 1) PCGB_TRY(pcgb_allreduce_sum(s->comm, s->red + 6, 2, st));
-  return PCGB_OK;
+  s->launches += 1;
+  return reduce_to_device(s, grid, 2, 6, st);
 }
 
-// one PCG iteration enqueued on st (pcg_solver.py:438-562); every kernel no-ops once the state is frozen
+// one PCG iteration enqueued on st (pcg_solver.py:438-562); every kernel no-ops once the state is frozen.
+// ev[0..4): optional event brackets around the SpMV launch(es) of this iteration (time_kernels).
 int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, double *xb0, double *resvec, cudaStream_t st, int *nl,
-                      cudaEvent_t ka = nullptr, cudaEvent_t kb = nullptr) {
+                      cudaEvent_t *ev = nullptr) {
   const int64_t n = s->n;
   const int vg = vec_grid(n);
-  const bool multi = s->comm && s->comm->nranks > 1;
+  const bool multi = multi_rank(s);
+  const bool peer = peer_path(s);
   k_pupdate<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, minv, s->p);
   PCGB_CHECK_LAUNCH();
   *nl += 1;
@@ -572,28 +842,57 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   // (p is consistent on shared dofs and K = sum of the subdomain matrices); see DESIGN.md.
   const double *pq_src;
   int pq_cnt;
-  if (s->E) {  // experimental matrix-free operator: product, then a separate unweighted dot of the local product
-    if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
+  bool halo_done = false;
+  if (s->E) {  // matrix-free operator: product, then a separate unweighted dot of the local product
+    if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
     PCGB_TRY(ebe_apply(s->E->P, s->p, s->q, st, nl, &s->d_ctrl->state));
-    if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
+    if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
     k_dot_w<<<vg, kVecBlock, 0, st>>>(n, s->p, s->q, nullptr, s->partials);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
     pq_src = s->partials; pq_cnt = vg;
   } else {
     const CsrPlan &P = s->A->P;
-    if (ka) PCGB_CUDA(cudaEventRecord(ka, st));
-    PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
-    if (kb) PCGB_CUDA(cudaEventRecord(kb, st));
-    pq_src = P.dot_partials;
-    pq_cnt = P.persist ? P.grid_persist : P.ntiles;
-    if (pq_cnt > 8192) {
-      const int sb = (pq_cnt + 4095) / 4096;
-      k_stage_reduce<<<sb, 256, 0, st>>>(P.dot_partials, pq_cnt, s->stage);
-      PCGB_CHECK_LAUNCH();
-      *nl += 1;
-      pq_src = s->stage; pq_cnt = sb;
+    if (peer && s->halo && s->halo->m > 0 && spmv_split_available(P)) {
+      // interface tiles -> pack (peer stores fly over NVLink) -> interior tiles; the unpack follows the p.q all-reduce
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
+      PCGB_TRY(spmv_launch_part(P, 0, s->p, s->q, true, st, nl, &s->d_ctrl->state));
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
+      PCGB_TRY(halo_pack(s->halo, s->q, st, nl));
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[2], st));
+      PCGB_TRY(spmv_launch_part(P, 1, s->p, s->q, true, st, nl, &s->d_ctrl->state));
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[3], st));
+      pq_src = P.dot_partials_split; pq_cnt = spmv_split_dot_count(P);
+      halo_done = true;
+    } else {
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
+      PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
+      if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
+      pq_src = P.dot_partials;
+      pq_cnt = P.persist ? P.grid_persist : P.ntiles;
+      if (pq_cnt > 8192) {
+        const int sb = (pq_cnt + 4095) / 4096;
+        k_stage_reduce<<<sb, 256, 0, st>>>(P.dot_partials, pq_cnt, s->stage);
+        PCGB_CHECK_LAUNCH();
+        *nl += 1;
+        pq_src = s->stage; pq_cnt = sb;
+      }
     }
+  }
+  if (peer) {
+    // own kernels over peer memory: the all-reduce is fused into the reduction kernel, the scalar logic follows in the same CTA
+    if (s->halo && !halo_done) PCGB_TRY(halo_pack(s->halo, s->q, st, nl));
+    const PeerWin win = s->comm->window();
+    k_reduce_ar<1, 1><<<1, 256, 0, st>>>(win, s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
+    PCGB_CHECK_LAUNCH();
+    *nl += 1;
+    if (s->halo) PCGB_TRY(halo_unpack(s->halo, s->q, st, nl));
+    k_update<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, s->q, s->p, minv, w, xb0, s->xalt, s->partials);
+    PCGB_CHECK_LAUNCH();
+    k_reduce_ar<5, 2><<<1, 256, 0, st>>>(win, s->d_ctrl, s->partials, vg, kMaxVecGrid, s->red + 1, resvec);
+    PCGB_CHECK_LAUNCH();
+    *nl += 2;
+    return PCGB_OK;
   }
   if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
   if (!multi) {
@@ -603,7 +902,7 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   } else {
     k_reduce<1, 0><<<1, 256, 0, st>>>(s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();
-    PCGB_TRY(pcgb_allreduce_sum(s->comm, s->red, 1, st));
+    PCGB_TRY(allreduce_sum(s->comm, s->red, 1, st));
     k_ctrl_alpha<<<1, 1, 0, st>>>(s->d_ctrl, s->red);
     PCGB_CHECK_LAUNCH();
     *nl += 2;
@@ -618,7 +917,7 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   } else {
     k_reduce<5, 0><<<1, 256, 0, st>>>(s->d_ctrl, s->partials, vg, kMaxVecGrid, s->red + 1, nullptr);
     PCGB_CHECK_LAUNCH();
-    PCGB_TRY(pcgb_allreduce_sum(s->comm, s->red + 1, 5, st));
+    PCGB_TRY(allreduce_sum(s->comm, s->red + 1, 5, st));
     k_ctrl_norms<<<1, 1, 0, st>>>(s->d_ctrl, s->red + 1, resvec);
     PCGB_CHECK_LAUNCH();
     *nl += 2;
@@ -628,7 +927,10 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
 
 int fetch_ctrl(pcgb_solver_t s, cudaStream_t st) {
   PCGB_CUDA(cudaMemcpyAsync(s->h_ctrl, s->d_ctrl, sizeof(PcgCtrl), cudaMemcpyDeviceToHost, st));
+  if (s->comm && s->comm->d_status) PCGB_CUDA(cudaMemcpyAsync(s->comm->h_status, s->comm->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
   PCGB_CUDA(cudaStreamSynchronize(st));
+  if (s->comm && s->comm->d_status && *s->comm->h_status != 0)
+    return fail(PCGB_ERR_COMM, "a peer-memory exchange timed out waiting for another rank (rank %d of %d)", s->comm->rank, s->comm->nranks);
   return PCGB_OK;
 }
 
@@ -672,28 +974,36 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   // the loop works on the solver's own pair of x buffers (graph / kernel arguments never change between solves)
   double *const xw = s->xown;
   double *xbuf[2] = {xw, s->xalt};
+  PCGB_CUDA(cudaEventRecord(s->ev_s0, st));
 
-  // ---- ||b||  (pcg_solver.py:381-384)
+  // ---- ||b||  (pcg_solver.py:381-384) and the initial residual (:408-418) with ONE host synchronisation:
+  //      sum b*b*w -> red[7], r = b - A x0 and sum r*r*w -> red[6]
   k_dot_w<<<vg, kVecBlock, 0, st>>>(n, d_b, d_b, d_w, s->partials);
   PCGB_CHECK_LAUNCH();
   s->launches += 1;
-  PCGB_TRY(reduce_to_host(s, vg, 1, st));
-  const double n2b = std::sqrt(s->h_red[0]);
+  PCGB_TRY(reduce_to_device(s, vg, 1, 7, st));
+  if (opt->x0_zero) {
+    // the caller states x0 = 0: A x0 = 0 exactly, hence r = b and ||r|| = ||b|| bit for bit - no operator application
+    PCGB_CUDA(cudaMemsetAsync(xw, 0, (size_t)n * sizeof(double), st));
+    PCGB_CUDA(cudaMemcpyAsync(s->r, d_b, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PCGB_CUDA(cudaMemcpyAsync(s->red + 6, s->red + 7, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  } else {
+    PCGB_CUDA(cudaMemcpyAsync(xw, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PCGB_TRY(true_residual_dev(s, d_b, d_w, xw, 6, st));
+    ++matvecs;
+  }
+  if (d_resvec) {  // ResVec[0] = sqrt(red[6]) (:431), computed on the device
+    k_sqrt_store<<<1, 1, 0, st>>>(s->red + 6, d_resvec);
+    PCGB_CHECK_LAUNCH();
+  }
+  PCGB_TRY(fetch_red(s, st));
+  const double n2b = std::sqrt(s->h_red[1]);
+  const double normr = std::sqrt(s->h_red[0]);
   const double tolb = opt->tol * n2b;
   res->normb = n2b;
   if (n2b == 0.0) {  // :387-395 - returns the initial guess, flag 0, relres 0, iter 0
     res->flag = 0; res->relres = 0.0; res->iters = 0; res->launches = s->launches;
     return PCGB_OK;
-  }
-  // ---- initial residual (:408-418)
-  double normr = 0.0;
-  PCGB_CUDA(cudaMemcpyAsync(xw, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  PCGB_TRY(true_residual(s, d_b, d_w, xw, &normr, st));
-  ++matvecs;
-  if (d_resvec) {
-    s->h_red[2] = normr;  // ResVec[0] (:431)
-    PCGB_CUDA(cudaMemcpyAsync(d_resvec, &s->h_red[2], sizeof(double), cudaMemcpyHostToDevice, st));
-    PCGB_CUDA(cudaStreamSynchronize(st));
   }
   if (!opt->fixed_iters && normr <= tolb) {  // :421-426
     res->flag = 0; res->relres = normr / n2b; res->iters = 0; res->matvecs = matvecs; res->launches = s->launches;
@@ -710,10 +1020,11 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   c.normr = normr; c.normr_act = normr; c.normrmin = normr;
   c.tolb = tolb; c.n2b = n2b; c.eps = 2.220446049250313e-16;
   c.state = ST_RUN; c.flag = 1; c.iter = 0; c.stag = 0; c.moresteps = 0; c.imin = 0; c.xcur = 0; c.xmin = 0;
+  c.alias = 1;   // MP_XMin = MP_X (:379-380): the same array until the first improvement is recorded
   c.maxiter = opt->maxiter; c.maxstag = maxstag; c.fixed_iters = opt->fixed_iters ? 1 : 0;
   *s->h_ctrl = c;
+  // (pinned source, stream-ordered: the next write to h_ctrl is the D2H copy of fetch_ctrl on the same stream)
   PCGB_CUDA(cudaMemcpyAsync(s->d_ctrl, s->h_ctrl, sizeof(PcgCtrl), cudaMemcpyHostToDevice, st));
-  PCGB_CUDA(cudaStreamSynchronize(st));
   // head of iteration 0: rho = z.r (:446-469)
   PCGB_TRY(rz_to_device(s, d_minv, d_w, st));
   k_ctrl_head<<<1, 1, 0, st>>>(s->d_ctrl, s->red + 6, 0);
@@ -723,7 +1034,8 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   int batch = opt->check_every > 0 ? opt->check_every : 16;
   if (batch > opt->maxiter) batch = opt->maxiter;
   const bool want_graph = opt->use_graph != 0 && !opt->time_kernels;
-  size_t kpairs = 0;
+  size_t ktimed = 0;           // iterations whose SpMV launches carry event brackets
+  int ev_per_iter = 2;
   PCGB_CUDA(cudaEventRecord(s->ev_l0, st));
   int flag = 1;
   int too_small = 0;
@@ -749,14 +1061,16 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
       PCGB_CUDA(cudaGraphLaunch(s->gexec, st));
       graph_launch_kernels += (int64_t)s->launches_per_iter * batch;
     } else {
+      const bool split = !s->E && peer_path(s) && s->halo && s->halo->m > 0 && spmv_split_available(s->A->P);
+      ev_per_iter = split ? 4 : 2;
       for (int k = 0; k < batch; ++k) {
         int nl = 0;
-        cudaEvent_t ka = nullptr, kb = nullptr;
-        if (opt->time_kernels && kpairs < 1024) {
-          while (s->ev_k.size() < 2 * (kpairs + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
-          ka = s->ev_k[2 * kpairs]; kb = s->ev_k[2 * kpairs + 1]; ++kpairs;
+        cudaEvent_t *ev = nullptr;
+        if (opt->time_kernels && ktimed < 1024) {
+          while (s->ev_k.size() < 4 * (ktimed + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
+          ev = &s->ev_k[4 * ktimed]; ++ktimed;
         }
-        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl, ka, kb));
+        PCGB_TRY(enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl, ev));
         s->launches += nl;
       }
     }
@@ -775,13 +1089,12 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
       if (c.moresteps >= maxmsteps) {                           // :548-552 (the reference raises here)
         too_small = 1; flag = 3; c.flag = 3; break;
       }
-      if (normr_act < c.normrmin) { c.normrmin = normr_act; c.xmin = c.xcur; c.imin = c.iter; }  // :555-558
+      if (normr_act < c.normrmin) { c.normrmin = normr_act; c.xmin = c.xcur; c.imin = c.iter; c.alias = 0; }  // :555-558
       if (c.stag >= maxstag) { flag = 3; c.flag = 3; break; }  // :560-562
       // continue with the replaced residual: head of the next iteration
       c.state = ST_RUN;
       *s->h_ctrl = c;
       PCGB_CUDA(cudaMemcpyAsync(s->d_ctrl, s->h_ctrl, sizeof(PcgCtrl), cudaMemcpyHostToDevice, st));
-      PCGB_CUDA(cudaStreamSynchronize(st));
       PCGB_TRY(rz_to_device(s, d_minv, d_w, st));
       k_ctrl_head<<<1, 1, 0, st>>>(s->d_ctrl, s->red + 6, 1);
       PCGB_CHECK_LAUNCH();
@@ -793,16 +1106,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
     break;
   }
   PCGB_CUDA(cudaEventRecord(s->ev_l1, st));
-  PCGB_CUDA(cudaEventSynchronize(s->ev_l1));
-  {
-    float ms = 0.f;
-    PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_l0, s->ev_l1));
-    res->loop_ms = ms;
-    res->loop_iters = c.iter + 1;
-    double tot = 0.0;
-    for (size_t k = 0; k < kpairs; ++k) { float t = 0.f; PCGB_CUDA(cudaEventElapsedTime(&t, s->ev_k[2 * k], s->ev_k[2 * k + 1])); tot += t; }
-    res->spmv_ms = tot; res->spmv_timed = (int64_t)kpairs;
-  }
 
   // ---- finalisation (:566-584)
   const int i = c.iter;
@@ -814,6 +1117,7 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
     iter_out = i;
     xout = c.xcur;
   } else {
+    // XMin is the current iterate while it is still aliased to X (no improvement recorded yet): c.xmin == c.xcur then
     double normr_min = 0.0;
     PCGB_TRY(true_residual(s, d_b, d_w, xbuf[c.xmin], &normr_min, st));
     ++matvecs;
@@ -823,7 +1127,26 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   }
   iter_out += 1;  // :584
   PCGB_CUDA(cudaMemcpyAsync(d_x, xbuf[xout], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  PCGB_CUDA(cudaStreamSynchronize(st));
+  PCGB_CUDA(cudaEventRecord(s->ev_s1, st));
+  PCGB_CUDA(cudaEventSynchronize(s->ev_s1));
+  {
+    float ms = 0.f;
+    PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_l0, s->ev_l1));
+    res->loop_ms = ms;
+    res->loop_iters = c.iter + 1;
+    PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_s0, s->ev_l0));
+    res->setup_ms = ms;
+    PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_l1, s->ev_s1));
+    res->final_ms = ms;
+    double tot = 0.0;
+    for (size_t k = 0; k < ktimed; ++k)
+      for (int e = 0; e + 1 < ev_per_iter; e += 2) {
+        float t = 0.f;
+        PCGB_CUDA(cudaEventElapsedTime(&t, s->ev_k[4 * k + e], s->ev_k[4 * k + e + 1]));
+        tot += t;
+      }
+    res->spmv_ms = tot; res->spmv_timed = (int64_t)ktimed;
+  }
   res->flag = flag; res->iters = iter_out; res->relres = relres; res->imin = c.imin; res->stag = c.stag;
   res->moresteps = c.moresteps; res->too_small_tol = too_small;
   // matvecs inside the loop = iterations started

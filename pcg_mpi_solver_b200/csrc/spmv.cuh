@@ -67,7 +67,17 @@ struct CsrPlan {
   // persistent pipelined variant (k_spmv_persist)
   bool persist = false;
   struct TileDesc *tile_desc = nullptr;  // [ntiles]
-  int stages = 0, stage_bytes = 0, smem_persist = 0, grid_persist = 0;
+  int stages = 0, stage_bytes = 0, smem_persist = 0, grid_persist = 0, ctas_per_sm = 1;
+  // column-triple index ("T3"): when every row is a sequence of aligned triples of consecutive staged positions
+  // (3 dofs per node: hex / concrete), ONE 16-bit index is stored per triple -> 8 + 2/3 bytes per non-zero
+  bool t3 = false;
+  uint16_t *lidx3 = nullptr;       // [nnz/3 + 16]
+  // interface-first split (multi-GPU overlap): tiles that own an interface row are listed first in desc_split
+  struct TileDesc *desc_split = nullptr;  // [ntiles] permutation of tile_desc
+  int nb_tiles = 0;                       // leading boundary tiles of desc_split
+  double *dot_partials_split = nullptr;   // [2 * grid_persist]
+  // the caller may drop `col` once the selected kernel no longer reads it (diag cached first)
+  double *diag_cache = nullptr;
 };
 
 // ------------------------------------------------------------------ PTX wrappers (TMA bulk copy)
@@ -534,7 +544,10 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int LANES, bool DOT, typename RP>
+// T3 = column-triple index: sidx holds ONE 16-bit staged position per aligned triple of non-zeros (k0 % 3 == 0 for
+// every tile because the plan is row-snapped and every row length is a multiple of 3); a lane owns whole triples:
+// 1 index load + 3 value loads (stride 3 doubles across lanes: conflict-free over 16 lanes) + 3 x loads per 3 FMAs.
+template <int LANES, bool DOT, bool T3, typename RP>
 __global__ void __launch_bounds__(kPersistThreads)
 k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx, const double *__restrict__ val,
                const double *__restrict__ x, double *__restrict__ y, const TileDesc *__restrict__ desc,
@@ -554,9 +567,10 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
   }
   __syncthreads();
 
-  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | (cap_rows f64, unused) | srp[cap_rows+2] i64 | sidx[cap_nnz] u16 | meta[8] i32
-  const size_t off_sx = (size_t)cap_nnz * 8, off_sxr = off_sx + (size_t)cap_x * 8, off_srp = off_sxr + (size_t)cap_rows * 8;
-  const size_t off_sidx = off_srp + (size_t)(cap_rows + 2) * 8, off_meta = off_sidx + (size_t)cap_nnz * 2;
+  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | srp[cap_rows+2] i64 | sidx (u16: cap_nnz, or cap_nnz/3+16 for T3) | meta[8] i32
+  const int cap_idx = T3 ? (cap_nnz / 3 + 16) : cap_nnz;
+  const size_t off_sx = (size_t)cap_nnz * 8, off_srp = off_sx + (size_t)cap_x * 8;
+  const size_t off_sidx = off_srp + (size_t)(cap_rows + 2) * 8, off_meta = (off_sidx + (size_t)cap_idx * 2 + 15) & ~(size_t)15;
 
   if (warp >= kConsWarps) {
     // ================= producer warp p: tiles it = p, p + kProd, ... (stage = it % stages, stages % kProd == 0)
@@ -602,7 +616,17 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
         const int64_t lim = nnz & ~(int64_t)kAlignMask;
         if (kend > lim) kend = lim;
         const int nb = (int)(kend - ka);
-        if (nb > 0) {
+        int toff = 0;
+        if (T3) {
+          // lidx3 is padded by 16 entries, so the aligned window [ta, tend) never leaves the array
+          const int64_t t0 = k0 / 3, ta = t0 & ~(int64_t)kAlignMask;
+          const int64_t tend = (t0 + cnt / 3 + kAlignMask) & ~(int64_t)kAlignMask;
+          const uint32_t ib = (uint32_t)(tend - ta) * 2u;
+          toff = (int)(t0 - ta);
+          mbar_expect_tx(&full_bar[s], (nb > 0 ? (uint32_t)nb * 8u : 0u) + ib);
+          if (nb > 0) bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &full_bar[s], pol);
+          if (ib > 0) bulk_g2s(sidx, lidx + ta, ib, &full_bar[s], pol);
+        } else if (nb > 0) {
           mbar_expect_tx(&full_bar[s], (uint32_t)nb * 10u);
           bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &full_bar[s], pol);
           bulk_g2s(sidx, lidx + ka, (uint32_t)nb * 2u, &full_bar[s], pol);
@@ -610,12 +634,15 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
           mbar_arrive(&full_bar[s]);
         }
         meta[0] = r0; meta[1] = Rraw; meta[2] = tile; meta[3] = cnt;
-        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32);
+        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32); meta[6] = toff;
       }
       {
         const int64_t lim = nnz & ~(int64_t)kAlignMask;
         const int64_t kt = (lim > ka ? lim : ka) + lane;
-        if (lane <= kAlignMask && kt >= lim && kt < k1) { sval[kt - ka] = val[kt]; sidx[kt - ka] = lidx[kt]; }
+        if (lane <= kAlignMask && kt >= lim && kt < k1) {
+          sval[kt - ka] = val[kt];
+          if (!T3) sidx[kt - ka] = lidx[kt];
+        }
       }
       // raw row offsets and the x entries of the tile's own rows: asynchronous copies
       for (int i = lane; i <= R; i += 32) cp_async<sizeof(RP)>(srp + i, rowptr + r0 + i);
@@ -667,6 +694,8 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
     const int k0l = (int)(k0 - ka), k1l = k0l + cnt;
     const int R = Rraw & 0x7fffffff;
     const bool head = Rraw < 0;
+    const uint16_t *sidt = sidx + (T3 ? meta[6] : 0);   // T3: triple t of the tile sits at sidt[t]
+    const double *svt = sval + k0l;                     //     and its values at svt[3 t .. 3 t + 2]
     for (int i0 = 0; i0 < R; i0 += G) {  // CTA-uniform trip count (full-mask shuffles)
       const int i = i0 + gid;  // (rows 8 apart per half-warp pair was tried: fewer bank conflicts, but slower - loses the x broadcast)
       const bool live = i < R;
@@ -679,15 +708,42 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
         e = (int)(ve < k0l ? k0l : (ve > k1l ? k1l : ve));
       }
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-      int j = a + gl;
-      for (; j + 3 * LANES < e; j += 4 * LANES) {
-        const double x0 = sx[sidx[j]], x1 = sx[sidx[j + LANES]], x2 = sx[sidx[j + 2 * LANES]], x3 = sx[sidx[j + 3 * LANES]];
-        acc0 = fma(sval[j], x0, acc0);
-        acc1 = fma(sval[j + LANES], x1, acc1);
-        acc2 = fma(sval[j + 2 * LANES], x2, acc2);
-        acc3 = fma(sval[j + 3 * LANES], x3, acc3);
+      if (T3) {
+        // row segment in triples of the tile
+        const int ta = (int)((unsigned)(a - k0l) / 3u), te = (int)((unsigned)(e - k0l) / 3u);
+        double acc4 = 0.0, acc5 = 0.0;
+        int t = ta + gl;
+        for (; t + LANES < te; t += 2 * LANES) {
+          const int ia = sidt[t], ib = sidt[t + LANES];
+          const double *va = svt + 3 * t, *vb = svt + 3 * (t + LANES);
+          const double xa0 = sx[ia], xa1 = sx[ia + 1], xa2 = sx[ia + 2];
+          const double xb0 = sx[ib], xb1 = sx[ib + 1], xb2 = sx[ib + 2];
+          acc0 = fma(va[0], xa0, acc0);
+          acc1 = fma(va[1], xa1, acc1);
+          acc2 = fma(va[2], xa2, acc2);
+          acc3 = fma(vb[0], xb0, acc3);
+          acc4 = fma(vb[1], xb1, acc4);
+          acc5 = fma(vb[2], xb2, acc5);
+        }
+        if (t < te) {
+          const int ia = sidt[t];
+          const double *va = svt + 3 * t;
+          acc0 = fma(va[0], sx[ia], acc0);
+          acc1 = fma(va[1], sx[ia + 1], acc1);
+          acc2 = fma(va[2], sx[ia + 2], acc2);
+        }
+        acc0 += acc3; acc1 += acc4; acc2 += acc5; acc3 = 0.0;
+      } else {
+        int j = a + gl;
+        for (; j + 3 * LANES < e; j += 4 * LANES) {
+          const double x0 = sx[sidx[j]], x1 = sx[sidx[j + LANES]], x2 = sx[sidx[j + 2 * LANES]], x3 = sx[sidx[j + 3 * LANES]];
+          acc0 = fma(sval[j], x0, acc0);
+          acc1 = fma(sval[j + LANES], x1, acc1);
+          acc2 = fma(sval[j + 2 * LANES], x2, acc2);
+          acc3 = fma(sval[j + 3 * LANES], x3, acc3);
+        }
+        for (; j < e; j += LANES) acc0 = fma(sval[j], sx[sidx[j]], acc0);
       }
-      for (; j < e; j += LANES) acc0 = fma(sval[j], sx[sidx[j]], acc0);
       const double acc = group_sum<LANES>((acc0 + acc1) + (acc2 + acc3));
       if (live && gl == 0) {
         if (i == 0 && head) carry[tile] = acc;
@@ -709,6 +765,41 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
       if (lane == 0) dot_partials[blockIdx.x] = t;
     }
   }
+}
+
+// ---- T3 plan helpers
+// every row offset a multiple of 3  <=>  every row length a multiple of 3 (rowptr[0] = 0)
+template <typename RP>
+__global__ void k_rows_mod3(const RP *__restrict__ rowptr, int64_t nrows, int *__restrict__ fail) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= nrows; r += (int64_t)gridDim.x * blockDim.x)
+    if (((int64_t)rowptr[r]) % 3 != 0) { *fail = 1; return; }
+}
+// one 16-bit staged position per aligned triple; fails unless the three positions are consecutive
+__global__ void k_build_idx3(const uint16_t *__restrict__ lidx, int64_t ntrip, uint16_t *__restrict__ lidx3, int *__restrict__ fail) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ntrip; t += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned a = lidx[3 * t], b = lidx[3 * t + 1], c = lidx[3 * t + 2];
+    if (b != a + 1 || c != a + 2) *fail = 1;
+    lidx3[t] = (uint16_t)a;
+  }
+}
+
+// ---- interface-first split: flag the tiles that own at least one marked row
+__global__ void k_mark_rows(const int *__restrict__ rows, int64_t count, unsigned char *__restrict__ rowflag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < count) rowflag[rows[i]] = 1;
+}
+__global__ void k_flag_tiles(const TileDesc *__restrict__ desc, int ntiles, const unsigned char *__restrict__ rowflag,
+                             unsigned char *__restrict__ tileflag) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ntiles) return;
+  const int r0 = desc[b].r0, R = desc[b].R & 0x7fffffff;
+  unsigned char f = 0;
+  for (int i = 0; i < R; ++i) f |= rowflag[r0 + i];
+  tileflag[b] = f;
+}
+__global__ void k_gather_desc(const TileDesc *__restrict__ desc, const int *__restrict__ perm, int ntiles, TileDesc *__restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < ntiles) out[b] = desc[perm[b]];
 }
 
 // rows that span several tiles: y[row] (written by the tile where the row starts) += carries, in tile order
@@ -887,7 +978,25 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
                                                                   P.tile_desc);
           PCGB_CHECK_LAUNCH();
           PCGB_CUDA(cudaStreamSynchronize(st));
-          P.stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + P.cap_rows * 8 + (P.cap_rows + 2) * 8 + P.cap_nnz * 2 + 32;
+          // column-triple index: row-snapped plan, every row offset a multiple of 3, every aligned triple consecutive
+          P.t3 = false;
+          if (P.snap && P.nnz % 3 == 0 && P.nnz >= 3 && env_int("PCGB_SPMV_T3", 1) != 0) {
+            PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+            k_rows_mod3<RP><<<(int)std::min<int64_t>((P.nrows + 256) / 256, 148 * 8), 256, 0, st>>>(rp, P.nrows, d_fail);
+            PCGB_CHECK_LAUNCH();
+            const int64_t ntrip = P.nnz / 3;
+            PCGB_CUDA(cudaMalloc(&P.lidx3, ((size_t)ntrip + 16) * sizeof(uint16_t)));
+            PCGB_CUDA(cudaMemsetAsync(P.lidx3 + ntrip, 0, 16 * sizeof(uint16_t), st));
+            k_build_idx3<<<(int)std::min<int64_t>((ntrip + 255) / 256, 148 * 16), 256, 0, st>>>(P.lidx, ntrip, P.lidx3, d_fail);
+            PCGB_CHECK_LAUNCH();
+            int h_f3 = 1;
+            PCGB_CUDA(cudaMemcpyAsync(&h_f3, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCGB_CUDA(cudaStreamSynchronize(st));
+            P.t3 = h_f3 == 0;
+            if (!P.t3) { cudaFree(P.lidx3); P.lidx3 = nullptr; }
+          }
+          const int cap_idx = P.t3 ? (P.cap_nnz / 3 + 16) : P.cap_nnz;
+          P.stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + (P.cap_rows + 2) * 8 + ((cap_idx * 2 + 15) & ~15) + 32;
           P.stage_bytes = (P.stage_bytes + 127) & ~127;
           int stages = env_int("PCGB_SPMV_STAGES", 4);
           if (stages < kProd) stages = kProd;
@@ -900,7 +1009,21 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           // resident CTAs per SM that really fit (227 KB of shared memory per SM, ~1 KB static per CTA)
           int fit = (227 * 1024) / (P.smem_persist + 2048);
           if (fit < 1) fit = 1;
-          P.grid_persist = std::min(P.ntiles, num_sms() * std::min(ctas > 0 ? ctas : 1, fit));
+          P.ctas_per_sm = std::min(ctas > 0 ? ctas : 1, fit);
+          P.grid_persist = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
+          if (P.persist) {
+            PCGB_CUDA(cudaMalloc(&P.dot_partials_split, (size_t)2 * (size_t)std::max(P.grid_persist, 1) * sizeof(double)));
+            if (P.t3) {
+              cudaFree(P.lidx); P.lidx = nullptr;   // the persistent T3 kernel is the only consumer of the indices
+              // lanes per row: a lane owns whole triples; 16 lanes at stride 3 doubles read the values conflict-free
+              const double t_avg = avg / 3.0;
+              int l3 = t_avg <= 6.0 ? 4 : t_avg <= 12.0 ? 8 : t_avg <= 40.0 ? 16 : 32;
+              l3 = env_int("PCGB_SPMV_LANES3", l3);
+              if (l3 == 4 || l3 == 8 || l3 == 16 || l3 == 32) P.lanes = l3;
+            }
+          } else if (P.t3) {
+            cudaFree(P.lidx3); P.lidx3 = nullptr; P.t3 = false;
+          }
         }
       }
     }
@@ -966,29 +1089,47 @@ inline int launch_staged_lanes(const CsrPlan &P, const double *x, double *y, cud
   }
 }
 
-template <int LANES, bool DOT, typename RP>
-inline int launch_persist_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
-  auto kern = k_spmv_persist<LANES, DOT, RP>;
-  if (P.ntiles == 0) return PCGB_OK;
+// one launch of the persistent kernel over the tiles desc[0..ntiles) with `grid` resident CTAs; dot partials -> dotp[0..grid)
+template <int LANES, bool DOT, bool T3, typename RP>
+inline int launch_persist_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
+                               int ntiles, int grid, double *dotp) {
+  auto kern = k_spmv_persist<LANES, DOT, T3, RP>;
   if (skip == reinterpret_cast<const int *>(1)) {
     PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return PCGB_OK;
   }
-  kern<<<P.grid_persist, kPersistThreads, P.smem_persist, st>>>(static_cast<const RP *>(P.rowptr), P.lidx, P.val, x, y, P.tile_desc,
-                                                                 P.win_start, P.win_off, P.ntiles, P.nnz, P.cap_nnz, P.cap_rows, P.cap_x,
-                                                                 P.stages, P.stage_bytes, P.carry, P.dot_partials, skip);
+  if (ntiles == 0) return PCGB_OK;
+  kern<<<grid, kPersistThreads, P.smem_persist, st>>>(static_cast<const RP *>(P.rowptr), T3 ? P.lidx3 : P.lidx, P.val, x, y, desc,
+                                                       P.win_start, P.win_off, ntiles, P.nnz, P.cap_nnz, P.cap_rows, P.cap_x,
+                                                       P.stages, P.stage_bytes, P.carry, dotp, skip);
   PCGB_CHECK_LAUNCH();
   return PCGB_OK;
 }
 
-template <bool DOT, typename RP>
-inline int launch_persist_lanes(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip) {
+template <bool DOT, bool T3, typename RP>
+inline int launch_persist_lanes(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
+                                int ntiles, int grid, double *dotp) {
   switch (P.lanes) {
-    case 4: return launch_persist_inst<4, DOT, RP>(P, x, y, st, skip);
-    case 8: return launch_persist_inst<8, DOT, RP>(P, x, y, st, skip);
-    case 32: return launch_persist_inst<32, DOT, RP>(P, x, y, st, skip);
-    default: return launch_persist_inst<16, DOT, RP>(P, x, y, st, skip);
+    case 4: return launch_persist_inst<4, DOT, T3, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    case 8: return launch_persist_inst<8, DOT, T3, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    case 32: return launch_persist_inst<32, DOT, T3, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    default: return launch_persist_inst<16, DOT, T3, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
   }
+}
+
+inline int launch_persist_any(const CsrPlan &P, const double *x, double *y, bool with_dot, cudaStream_t st, const int *skip,
+                              const TileDesc *desc, int ntiles, int grid, double *dotp) {
+  if (P.ntiles == 0) return PCGB_OK;
+  if (P.t3) {
+    if (P.rp64) return with_dot ? launch_persist_lanes<true, true, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                                : launch_persist_lanes<false, true, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    return with_dot ? launch_persist_lanes<true, true, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                    : launch_persist_lanes<false, true, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  }
+  if (P.rp64) return with_dot ? launch_persist_lanes<true, false, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                              : launch_persist_lanes<false, false, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  return with_dot ? launch_persist_lanes<true, false, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                  : launch_persist_lanes<false, false, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
 }
 
 // y = A x ; with_dot additionally leaves per-tile partials of x.y in P.dot_partials.
@@ -997,8 +1138,7 @@ inline int spmv_launch(const CsrPlan &P, const double *x, double *y, bool with_d
                        const int *skip = nullptr) {
   int rc;
   if (P.persist) {
-    if (P.rp64) rc = with_dot ? launch_persist_lanes<true, int64_t>(P, x, y, st, skip) : launch_persist_lanes<false, int64_t>(P, x, y, st, skip);
-    else rc = with_dot ? launch_persist_lanes<true, int32_t>(P, x, y, st, skip) : launch_persist_lanes<false, int32_t>(P, x, y, st, skip);
+    rc = launch_persist_any(P, x, y, with_dot, st, skip, P.tile_desc, P.ntiles, P.grid_persist, P.dot_partials);
   } else if (P.staged) {
     if (P.rp64) rc = with_dot ? launch_staged_lanes<true, int64_t>(P, x, y, st, skip) : launch_staged_lanes<false, int64_t>(P, x, y, st, skip);
     else rc = with_dot ? launch_staged_lanes<true, int32_t>(P, x, y, st, skip) : launch_staged_lanes<false, int32_t>(P, x, y, st, skip);
@@ -1021,6 +1161,60 @@ inline int spmv_launch(const CsrPlan &P, const double *x, double *y, bool with_d
   return PCGB_OK;
 }
 
+// ---- interface-first split (multi-GPU overlap) ------------------------------------------------------------
+// spmv_split_available(P): the persistent kernel is selected, no row spans tiles, and a boundary set was registered.
+inline bool spmv_split_available(const CsrPlan &P) { return P.persist && P.nfix == 0 && P.desc_split != nullptr; }
+
+// part 0: the tiles owning interface rows (launch BEFORE the halo pack); part 1: all other tiles (overlaps the
+// transfer).  With with_dot the partials of part k land in dot_partials_split[k * grid_persist ...); the caller
+// reduces spmv_split_dot_count(P) contiguous entries (unused slots are zero-filled at registration).
+inline int spmv_launch_part(const CsrPlan &P, int part, const double *x, double *y, bool with_dot, cudaStream_t st,
+                            int *launches = nullptr, const int *skip = nullptr) {
+  const int nt = part == 0 ? P.nb_tiles : P.ntiles - P.nb_tiles;
+  if (nt <= 0) return PCGB_OK;
+  const TileDesc *desc = P.desc_split + (part == 0 ? 0 : P.nb_tiles);
+  const int grid = std::min(nt, P.grid_persist);
+  PCGB_TRY(launch_persist_any(P, x, y, with_dot, st, skip, desc, nt, grid, P.dot_partials_split + (size_t)part * P.grid_persist));
+  if (launches) *launches += 1;
+  return PCGB_OK;
+}
+inline int spmv_split_dot_count(const CsrPlan &P) { return 2 * P.grid_persist; }
+
+// register the interface rows (device array of row indices) and build the boundary-first tile order
+inline int spmv_set_boundary_rows(CsrPlan &P, const int *d_rows, int64_t count, cudaStream_t st) {
+  if (!P.persist || P.nfix != 0 || P.ntiles == 0) return PCGB_OK;  // split not applicable: callers fall back to the serial order
+  unsigned char *rowflag = nullptr, *tileflag = nullptr;
+  int *d_perm = nullptr;
+  int rc = PCGB_OK;
+  std::vector<unsigned char> hflag((size_t)P.ntiles);
+  std::vector<int> perm((size_t)P.ntiles);
+  auto cleanup = [&]() { cudaFree(rowflag); cudaFree(tileflag); cudaFree(d_perm); };
+#define PCGB_SB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(PCGB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+  PCGB_SB(cudaMalloc(&rowflag, (size_t)P.nrows + 1));
+  PCGB_SB(cudaMalloc(&tileflag, (size_t)P.ntiles));
+  PCGB_SB(cudaMalloc(&d_perm, (size_t)P.ntiles * sizeof(int)));
+  PCGB_SB(cudaMemsetAsync(rowflag, 0, (size_t)P.nrows + 1, st));
+  if (count > 0) k_mark_rows<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_rows, count, rowflag);
+  k_flag_tiles<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.tile_desc, P.ntiles, rowflag, tileflag);
+  PCGB_SB(cudaGetLastError());
+  PCGB_SB(cudaMemcpyAsync(hflag.data(), tileflag, (size_t)P.ntiles, cudaMemcpyDeviceToHost, st));
+  PCGB_SB(cudaStreamSynchronize(st));
+  int nb = 0;
+  for (int b = 0; b < P.ntiles; ++b) if (hflag[(size_t)b]) perm[(size_t)nb++] = b;
+  int k = nb;
+  for (int b = 0; b < P.ntiles; ++b) if (!hflag[(size_t)b]) perm[(size_t)k++] = b;
+  if (!P.desc_split) PCGB_SB(cudaMalloc(&P.desc_split, (size_t)P.ntiles * sizeof(TileDesc)));
+  PCGB_SB(cudaMemcpyAsync(d_perm, perm.data(), (size_t)P.ntiles * sizeof(int), cudaMemcpyHostToDevice, st));
+  k_gather_desc<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.tile_desc, d_perm, P.ntiles, P.desc_split);
+  PCGB_SB(cudaGetLastError());
+  PCGB_SB(cudaMemsetAsync(P.dot_partials_split, 0, (size_t)2 * (size_t)std::max(P.grid_persist, 1) * sizeof(double), st));
+  PCGB_SB(cudaStreamSynchronize(st));
+#undef PCGB_SB
+  P.nb_tiles = nb;
+  cleanup();
+  return rc;
+}
+
 // raise the dynamic shared memory limit of the instantiations this plan will launch (done once at
 // plan time so that nothing but launches happens inside CUDA-graph capture)
 inline int spmv_configure(const CsrPlan &P) {
@@ -1034,7 +1228,7 @@ inline void free_plan(CsrPlan &P) {
   cudaFree(P.tile_row); cudaFree(P.tile_k); cudaFree(P.carry); cudaFree(P.dot_partials);
   cudaFree(P.fix_row); cudaFree(P.fix_first); cudaFree(P.fix_cnt);
   cudaFree(P.tile_xlen); cudaFree(P.tile_win); cudaFree(P.win_start); cudaFree(P.win_off); cudaFree(P.lidx);
-  cudaFree(P.tile_desc);
+  cudaFree(P.tile_desc); cudaFree(P.lidx3); cudaFree(P.desc_split); cudaFree(P.dot_partials_split); cudaFree(P.diag_cache);
 }
 
 }  // namespace pcgb

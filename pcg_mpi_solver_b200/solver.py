@@ -30,16 +30,59 @@ from . import _lib
 from .csr import CsrMatrix
 
 
-class Communicator:
-    """NCCL communicator of the solver ranks (one rank = one GPU = one subdomain, pcg_solver.py:91)."""
+def _allgather_bytes(blob: bytes, group=None):
+    """All-gather of one bytes object per rank over the torch.distributed side channel (rank order)."""
+    import torch.distributed as dist
+    box = [None] * dist.get_world_size(group)
+    dist.all_gather_object(box, blob, group=group)
+    return box
 
-    def __init__(self, rank: int, nranks: int, unique_id: bytes, device=None):
+
+class Communicator:
+    """Communicator of the solver ranks (one rank = one GPU = one subdomain, pcg_solver.py:91; replaces COMM_WORLD).
+
+    Data path (see include/pcgb200.h): `transport == "peer"` = the library's own kernels over CUDA-IPC mapped peer memory
+    (NVLink / NVSwitch; all-reduce fused into the reduction kernel, halo values stored straight into the neighbours'
+    buffers), `"nccl"` = ncclAllReduce / ncclSend / ncclRecv.  The host side channel (torch.distributed) only carries the
+    NCCL unique id and the IPC handles."""
+
+    def __init__(self, rank: int, nranks: int, unique_id: bytes | None, device=None, allgather=None):
         self.rank, self.nranks = rank, nranks
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self._h = ctypes.c_void_p()
-        uid = (ctypes.c_ubyte * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._allgather = allgather
+        self.peer_error = None
+        uid = (ctypes.c_ubyte * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().pcgb_comm_create(rank, nranks, uid, ctypes.byref(self._h)), "pcgb_comm_create")
+        if allgather is not None and nranks > 1:
+            self.exchange_windows(allgather)
+
+    def exchange_windows(self, allgather) -> bool:
+        """Export this rank's window, all-gather the handles, import the peers' windows.  On failure (no CUDA IPC in this
+        environment) the communicator stays on NCCL; the reason is kept in `peer_error`."""
+        lib = _lib.load()
+        self._allgather = allgather
+        self.peer_error = None
+        blob = (ctypes.c_ubyte * _lib.IPC_BLOB_BYTES)()
+        ok = True
+        with torch.cuda.device(self.device):
+            if lib.pcgb_comm_window_export(self._h, blob) != 0:
+                ok, self.peer_error = False, lib.pcgb_last_error().decode()
+        blobs = allgather(bytes(blob) if ok else b"")
+        if not all(len(b) == _lib.IPC_BLOB_BYTES for b in blobs):
+            return False                                   # some rank could not export: everybody stays on NCCL
+        buf = (ctypes.c_ubyte * (_lib.IPC_BLOB_BYTES * self.nranks)).from_buffer_copy(b"".join(blobs))
+        with torch.cuda.device(self.device):
+            rc = lib.pcgb_comm_window_import(self._h, buf)
+        if rc != 0:
+            self.peer_error = lib.pcgb_last_error().decode()
+        oks = allgather(b"1" if rc == 0 else b"0")
+        if not all(o == b"1" for o in oks):
+            if self.transport == "peer":                   # imported here but not everywhere: do not use it
+                lib.pcgb_comm_set_transport(self._h, _lib.TRANSPORT_NCCL)
+            return False
+        return True
 
     @staticmethod
     def unique_id() -> bytes:
@@ -48,18 +91,30 @@ class Communicator:
         return bytes(uid)
 
     @classmethod
-    def from_torch_distributed(cls, device=None):
-        """Bootstrap from an initialised torch.distributed group: rank 0 creates the NCCL unique id and
-        broadcasts it (side channel only; the data path uses the library's own communicator)."""
+    def from_torch_distributed(cls, device=None, nccl: bool = True, group=None):
+        """Bootstrap from an initialised torch.distributed group: rank 0 creates the NCCL unique id and broadcasts it,
+        then the peer windows are exchanged (side channel only; the data path uses the library's own communicator).
+        nccl=False builds a peer-only communicator (e.g. several ranks sharing one GPU in a test)."""
         import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
-        box = [cls.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        return cls(rank, world, box[0], device)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = None
+        if nccl:
+            box = [cls.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = box[0]
+        return cls(rank, world, uid, device, allgather=lambda b: _allgather_bytes(b, group))
 
     @property
     def handle(self):
         return self._h
+
+    @property
+    def transport(self) -> str:
+        return "peer" if _lib.load().pcgb_comm_transport(self._h) == _lib.TRANSPORT_PEER else "nccl"
+
+    def set_transport(self, name: str) -> None:
+        _lib.check(_lib.load().pcgb_comm_set_transport(self._h, _lib.TRANSPORT_PEER if name == "peer" else _lib.TRANSPORT_NCCL),
+                   "pcgb_comm_set_transport")
 
     def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
@@ -92,6 +147,8 @@ class SolveInfo:
     spmv_ms: float = 0.0
     spmv_timed: int = 0
     loop_iters: int = 0
+    setup_ms: float = 0.0
+    final_ms: float = 0.0
     resvec: np.ndarray | None = None
 
 
@@ -118,15 +175,23 @@ class SubdomainOperator:
         self._solver = ctypes.c_void_p()
         lib = _lib.load()
         with torch.cuda.device(self.device):
-            if comm is not None and len(self.nbr_ranks) > 0:
+            if comm is not None and comm.nranks > 1:
+                # every rank builds a plan (also one without neighbours): the peer-transport import is collective
                 nn = len(self.nbr_ranks)
-                ranks = (ctypes.c_int32 * nn)(*self.nbr_ranks)
+                ranks = (ctypes.c_int32 * max(nn, 1))(*self.nbr_ranks)
                 ptr = np.zeros(nn + 1, dtype=np.int64)
                 ptr[1:] = np.cumsum([len(v) for v in self.ovrlp])
-                idx = np.ascontiguousarray(np.concatenate(self.ovrlp)) if nn else np.zeros(0, dtype=np.int64)
+                idx = np.ascontiguousarray(np.concatenate(self.ovrlp)) if nn else np.zeros(1, dtype=np.int64)
                 _lib.check(lib.pcgb_halo_create(comm.handle, nn, ranks, ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.n,
                                                 ctypes.byref(self._halo)), "pcgb_halo_create")
+                if comm.transport == "peer" and comm._allgather is not None:
+                    nb = int(lib.pcgb_halo_blob_bytes(self._halo))
+                    blob = (ctypes.c_ubyte * nb)()
+                    _lib.check(lib.pcgb_halo_export(self._halo, blob), "pcgb_halo_export")
+                    blobs = comm._allgather(bytes(blob))
+                    buf = (ctypes.c_ubyte * (nb * comm.nranks)).from_buffer_copy(b"".join(blobs))
+                    _lib.check(lib.pcgb_halo_import(self._halo, buf), "pcgb_halo_import")
             create = lib.pcgb_solver_create if isinstance(A, CsrMatrix) else lib.pcgb_solver_create_ebe  # EbeMatrix: experimental
             _lib.check(create(A.handle, self._halo if self._halo else None,
                               comm.handle if comm is not None else None, ctypes.byref(self._solver)), "pcgb_solver_create")
@@ -168,7 +233,7 @@ class SubdomainOperator:
         opt = _lib.Options(tol=float(tol), maxiter=int(maxiter), n_global=int(self.n_global), max_stag=int(max_stag),
                            check_every=int(check_every), use_graph=1 if use_graph else 0,
                            fixed_iters=1 if fixed_iters else 0, record_resvec=1 if record_resvec else 0,
-                           time_kernels=1 if time_kernels else 0)
+                           time_kernels=1 if time_kernels else 0, x0_zero=1 if x0 is None else 0)
         res = _lib.Result()
         resvec = torch.zeros(maxiter + 2, dtype=torch.float64, device=dev) if record_resvec else None
         with torch.cuda.device(dev):
@@ -176,7 +241,7 @@ class SubdomainOperator:
                                       _lib.ptr(resvec), ctypes.byref(res), _lib.stream_ptr()), "pcgb_solve")
         info = SolveInfo(res.flag, res.iters, res.relres, res.normb, res.imin, res.stag, res.moresteps,
                          bool(res.too_small_tol), res.matvecs, res.launches, res.loop_ms, res.spmv_ms,
-                         res.spmv_timed, res.loop_iters)
+                         res.spmv_timed, res.loop_iters, res.setup_ms, res.final_ms)
         if record_resvec:
             info.resvec = resvec[: res.iters + 1].cpu().numpy()
         return x, info
