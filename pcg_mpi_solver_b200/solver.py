@@ -243,7 +243,7 @@ class SubdomainOperator:
                          bool(res.too_small_tol), res.matvecs, res.launches, res.loop_ms, res.spmv_ms,
                          res.spmv_timed, res.loop_iters, res.setup_ms, res.final_ms)
         if record_resvec:
-            info.resvec = resvec[: res.iters + 1].cpu().numpy()
+            info.resvec = resvec[: int(res.loop_iters) + 1].cpu().numpy()   # ||r_0|| .. ||r_k||, k = iterations executed
         return x, info
 
     def __del__(self):

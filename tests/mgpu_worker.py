@@ -58,12 +58,22 @@ def main():
     use_graph = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # PCGB_SHARED_GPU=1: all ranks drive cuda:0 (time-sliced) with a peer-only communicator - exercises the peer-memory
+    # halo / all-reduce kernels between OS processes on a ONE-GPU box (NCCL refuses two ranks on one device)
+    shared = os.environ.get("PCGB_SHARED_GPU", "0") == "1"
+    if shared:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    dist.init_process_group("nccl", device_id=dev)
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     from pcg_mpi_solver_b200.hexmesh import (block_grid, generate_matrix, interface_lists, load_vector, partition_blocks)
     from pcg_mpi_solver_b200.solver import Communicator, SubdomainOperator
-    comm = Communicator.from_torch_distributed(dev)
+    comm = Communicator.from_torch_distributed(dev, nccl=not shared)
+    if os.environ.get("PCGB_EXPECT_TRANSPORT"):
+        assert comm.transport == os.environ["PCGB_EXPECT_TRANSPORT"], (comm.transport, comm.peer_error)
     pgrid = block_grid(world)
     ng = tuple(block * pgrid[a] + (1 if a == 1 else 0) for a in range(3))  # uneven cut along y
     blocks = partition_blocks(ng, pgrid)
@@ -87,6 +97,9 @@ def main():
     y = op.apply(torch.from_numpy(v).to(dev)).cpu().numpy()
     wsum = torch.tensor([float(np.sum(w))], dtype=torch.float64, device=dev)
     comm.allreduce_sum(wsum)
+    # a second operator application AFTER the solve: the exchange epochs keep counting across graph replays and direct calls
+    y2 = op.apply(torch.from_numpy(v).to(dev)).cpu().numpy()
+    assert np.array_equal(y, y2), "operator application is not reproducible"
     gathered = [None] * world
     dist.gather_object({"gdof": gdof, "x": x.cpu().numpy(), "y": y, "w": w, "info": (info.flag, info.iters, info.relres)},
                        gathered if rank == 0 else None, dst=0)
@@ -118,7 +131,8 @@ def main():
                "x_rel_err": float(np.linalg.norm(U - Uref) / np.linalg.norm(Uref)),
                "y_rel_err": float(np.linalg.norm(Y - Yref) / np.linalg.norm(Yref)),
                "copy_mismatch": consistent / float(np.abs(U).max()), "weight_sum": float(wsum.item()), "n_global": n_global,
-               "halo_bytes": op.halo_bytes(), "all_infos": [g["info"] for g in gathered]}
+               "halo_bytes": op.halo_bytes(), "all_infos": [g["info"] for g in gathered], "transport": comm.transport,
+               "plan": A.plan_info(), "launches": info.launches, "loop_ms": info.loop_ms}
         with open(out_path, "w") as f:
             json.dump(res, f)
         print(json.dumps(res))

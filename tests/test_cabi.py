@@ -75,7 +75,7 @@ def test_bench_reference_arm_schema():
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["unit"] == "iterations/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["impl"] == "reference" and d["unit"].startswith("subdomain-iterations/s") and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]

@@ -45,3 +45,29 @@ def test_ebe_operator_concrete(cuda):
     assert float((ye - yc).abs().max() / yc.abs().max()) <= 1e-12
     xs, info = ebe.solve(torch.from_numpy(sub.b).to(cuda), ebe.jacobi(), 1e-7, 10000)
     assert info.flag == 0 and abs(info.iters - 1085) <= 2
+
+
+def test_two_live_ebe_operators_keep_their_own_pattern_matrices(cuda):
+    """The constant-memory slots of the 24-dof pattern matrices are shared per device: creating a second operator with a
+    DIFFERENT Ke must not disturb a live first one (slots are content-deduplicated and reference-counted)."""
+    import torch
+    from pcg_mpi_solver_b200.ebe import EbeMatrix
+    from pcg_mpi_solver_b200.hexmesh import HexBlock, generate_matrix, hex_type_group
+    ops, refs = [], []
+    for nu in (0.3, 0.1, 0.3, 0.45):                       # third one shares the first one's slot
+        blk = HexBlock((6, 5, 4), (0, 0, 0), (6, 5, 4), h=0.25, nu=nu)
+        grp, eff, ndof = hex_type_group(blk)
+        ops.append(EbeMatrix([grp], eff, ndof, device=cuda))
+        refs.append(generate_matrix(blk, device=cuda))
+    x = torch.randn(ops[0].shape[0], dtype=torch.float64, device=cuda)
+    for rounds in range(2):                                 # interleaved applications, all operators alive
+        for E, A in zip(ops, refs):
+            ye, yc = E.apply_local(x), A.spmv(x)
+            assert float((ye - yc).abs().max() / yc.abs().max()) <= 1e-12
+    del ops[1]                                               # releasing one operator leaves the others intact
+    blk = HexBlock((6, 5, 4), (0, 0, 0), (6, 5, 4), h=0.25, nu=0.2)
+    grp, eff, ndof = hex_type_group(blk)
+    extra = EbeMatrix([grp], eff, ndof, device=cuda)         # may reuse the freed slot
+    for E, A in zip(ops + [extra], [refs[0], refs[2], refs[3], generate_matrix(blk, device=cuda)]):
+        ye, yc = E.apply_local(x), A.spmv(x)
+        assert float((ye - yc).abs().max() / yc.abs().max()) <= 1e-12

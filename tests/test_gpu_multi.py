@@ -11,21 +11,46 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(world, tmp_path, block=6, graph=1, port=29517):
+def _run(world, tmp_path, block=6, graph=1, port=29517, env=None, timeout=600):
     out = tmp_path / f"mgpu_{world}.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), str(out), str(block), str(graph)]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-4000:]
     return json.loads(out.read_text())
 
 
+def _check(res):
+    assert res["flag"] == res["ref_flag"] == 0
+    assert abs(res["iters"] - res["ref_iters"]) <= 2
+    assert res["relres"] <= 1e-12
+    assert res["y_rel_err"] <= 1e-13          # operator + interface sum
+    assert res["x_rel_err"] <= 1e-9           # solution at tol 1e-12
+    assert res["copy_mismatch"] <= 1e-12      # shared dofs stay consistent across ranks
+    assert res["weight_sum"] == res["n_global"]  # ownership weights partition the free dofs
+    assert all(tuple(i) == tuple(res["all_infos"][0]) for i in res["all_infos"])  # every rank agrees
+
+
+@pytest.mark.parametrize("world,graph,block", [(2, 1, 6), (2, 0, 6), (4, 1, 5)])
+def test_peer_transport_ranks_sharing_one_gpu(cuda, tmp_path, world, graph, block):
+    """a13/a14 on a ONE-GPU box: `world` OS processes time-share cuda:0 and exchange through CUDA-IPC mapped memory with the
+    same kernels that run over NVLink between GPUs (fused all-reduce in k_reduce_ar, k_halo_pack_peer / k_halo_unpack_peer,
+    interface-first SpMV split), against the oracle's multi-part emulation of the reference (pcg_solver.py:303-334, 622-628)."""
+    res = _run(world, tmp_path, block=block, graph=graph, port=29617 + 2 * world + graph,
+               env={"PCGB_SHARED_GPU": "1", "PCGB_EXPECT_TRANSPORT": "peer"}, timeout=900)
+    assert res["transport"] == "peer"
+    _check(res)
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("world,graph", [(2, 1), (2, 0), (4, 1), (8, 1)])
-def test_multi_gpu_matches_oracle(cuda, tmp_path, world, graph):
+def test_multi_gpu_matches_oracle(cuda, tmp_path, world, graph, transport):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    res = _run(world, tmp_path, graph=graph, port=29517 + world + graph)
+    res = _run(world, tmp_path, graph=graph, port=29517 + world + graph + (40 if transport == "nccl" else 0),
+               env={"PCGB_COMM": transport, "PCGB_EXPECT_TRANSPORT": transport})
+    assert res["transport"] == transport
     assert res["flag"] == res["ref_flag"] == 0
     assert abs(res["iters"] - res["ref_iters"]) <= 2
     assert res["relres"] <= 1e-12

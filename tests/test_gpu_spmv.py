@@ -46,6 +46,7 @@ def test_spmv_variants(cuda, monkeypatch, lanes, variant):
     monkeypatch.setenv("PCGB_SPMV_TMA", "0" if variant == "ldg" else "1")
     monkeypatch.setenv("PCGB_SPMV_STAGE", "1" if variant in ("staged", "persist") else "0")
     monkeypatch.setenv("PCGB_SPMV_PERSIST", "1" if variant == "persist" else "0")
+    monkeypatch.setenv("PCGB_SPMV_T3", "0")     # one 16-bit index per non-zero (the column-triple mode has its own test)
     A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
     M = _check_spmv(A, cuda, seed=lanes)
     info = M.plan_info()
@@ -172,3 +173,97 @@ def test_diag_and_vector_kernels(cuda):
     np.testing.assert_allclose(yd.cpu().numpy(), 0.5 * a - 2.0 * b, rtol=1e-15, atol=1e-15)
     _lib.check(lib.pcgb_dot_w(0, None, None, None, _lib.ptr(out), _lib.stream_ptr()))  # empty input
     assert out.item() == 0.0
+
+
+@pytest.mark.parametrize("lanes3", [4, 8, 16, 32])
+@pytest.mark.parametrize("tile", [512, 2304])
+def test_spmv_triple_index(cuda, monkeypatch, lanes3, tile):
+    """Column-triple index: 3 dofs per node make every row a sequence of aligned triples of consecutive columns; the
+    persistent kernel then streams ONE 16-bit staged position per triple (8 + 2/3 B per non-zero instead of 10)."""
+    monkeypatch.setenv("PCGB_SPMV_LANES3", str(lanes3))
+    monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
+    A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
+    M = _check_spmv(A, cuda, seed=lanes3)
+    info = M.plan_info()
+    assert info["triple_index"] == 1 and info["staged"] == 2 and info["lanes"] == lanes3
+    assert M.stream_bytes() < 8.8 * A.nnz + 40 * A.shape[0] + 64 * info["ntiles"]
+    # an interior (unclamped) box and a box with a ragged last tile
+    _check_spmv(R.hex_box_csr((8, 6, 4), (4, 0, 2), (4, 3, 2)), cuda, seed=1)
+    # the fused dot epilogue of the PCG loop goes through the same kernel: compare x.(A x)
+    import torch
+    from pcg_mpi_solver_b200 import _lib
+    x = torch.from_numpy(np.random.default_rng(3).standard_normal(A.shape[0])).to(cuda)
+    M.set_boundary_rows(torch.arange(0, A.shape[0], 7, dtype=torch.int32, device=cuda))
+    y, d = M.spmv_split(x, with_dot=True)
+    y_ref = A @ x.cpu().numpy()
+    assert np.abs(y.cpu().numpy() - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    assert abs(float(d) - float(x.cpu().numpy() @ y_ref)) <= 1e-12 * float(np.abs(x.cpu().numpy()) @ np.abs(y_ref))
+
+
+def test_spmv_triple_index_not_applicable(cuda):
+    """Rows that are not made of column triples keep the per-non-zero index (Poisson: 27 single columns per row)."""
+    M = _check_spmv(R.poisson27(12), cuda)
+    assert M.plan_info()["triple_index"] == 0
+    # triples by count but not consecutive columns
+    rng = np.random.default_rng(5)
+    n = 300
+    rows = np.repeat(np.arange(n), 6)
+    cols = np.concatenate([np.sort(rng.choice(n, 6, replace=False)) for _ in range(n)])
+    A = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    M = _check_spmv(A, cuda, seed=2)
+    assert M.plan_info()["triple_index"] == 0
+
+
+@pytest.mark.parametrize("t3", ["0", "1"])
+def test_spmv_interface_first_split(cuda, monkeypatch, t3):
+    """Interface-first split (multi-GPU overlap): tiles owning a registered row run in a first launch, the rest in a
+    second one; y is bit-identical to the single launch (same tiles, same arithmetic), x.y agrees to rounding."""
+    import torch
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    monkeypatch.setenv("PCGB_SPMV_T3", t3)
+    monkeypatch.setenv("PCGB_SPMV_TILE", "512")
+    A = R.hex_box_csr((12, 10, 8), (0, 0, 0), (12, 10, 8))
+    n = A.shape[0]
+    M = CsrMatrix.from_scipy(A, device=cuda)
+    assert M.plan_info()["interface_tiles"] == -1
+    x = torch.from_numpy(np.random.default_rng(6).standard_normal(n)).to(cuda)
+    y0 = M.spmv(x).clone()
+    # the x = max face of the box: every 12th node -> scattered tiles; plus one whole z plane -> contiguous tiles
+    node = np.arange(n // 3)
+    face = np.nonzero((node % 12 == 11) | (node // (12 * 11) == 3))[0]
+    rows = (3 * face[:, None] + np.arange(3)[None, :]).ravel().astype(np.int32)
+    M.set_boundary_rows(torch.from_numpy(rows).to(cuda))
+    info = M.plan_info()
+    assert 0 < info["interface_tiles"] < info["ntiles"]
+    y1, d = M.spmv_split(x, with_dot=True)
+    assert torch.equal(y0, y1)
+    ref = float(torch.dot(x, y0))
+    assert abs(float(d) - ref) <= 1e-12 * float(torch.dot(x.abs(), y0.abs()))
+    # degenerate registrations: nothing / everything is interface
+    M.set_boundary_rows(torch.zeros(0, dtype=torch.int32, device=cuda))
+    assert M.plan_info()["interface_tiles"] == 0 and torch.equal(M.spmv_split(x), y0)
+    M.set_boundary_rows(torch.arange(n, dtype=torch.int32, device=cuda))
+    assert M.plan_info()["interface_tiles"] == M.plan_info()["ntiles"] and torch.equal(M.spmv_split(x), y0)
+
+
+def test_release_col(cuda):
+    """The persistent kernel never reads the 4-byte column array: after release_col() SpMV and the Jacobi diagonal still work."""
+    import torch
+    from pcg_mpi_solver_b200 import _lib
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
+    M = CsrMatrix.from_scipy(A, device=cuda)
+    x = torch.from_numpy(np.random.default_rng(7).standard_normal(A.shape[0])).to(cuda)
+    y0, d0 = M.spmv(x).clone(), M.diagonal().clone()
+    assert M.release_col() and M.col is None and M.plan_info()["col_released"] == 1
+    torch.cuda.empty_cache()
+    junk = torch.full((A.nnz,), -1, dtype=torch.int32, device=cuda)   # likely reuses the freed block
+    assert torch.equal(M.spmv(x), y0) and torch.equal(M.diagonal(), d0)
+    del junk
+    with pytest.raises(_lib.PcgbError):
+        M.to_scipy()
+    # a plan that gathers through L1 needs the columns: release is refused, nothing changes
+    P = CsrMatrix.from_scipy(R.poisson27(6), device=cuda)
+    if P.plan_info()["staged"] != 2:
+        assert not P.release_col() and P.col is not None
