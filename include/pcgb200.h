@@ -32,6 +32,7 @@ typedef struct pcgb_comm_s *pcgb_comm_t;   /* communicator: peer-memory windows 
 typedef struct pcgb_halo_s *pcgb_halo_t;   /* interface ("halo") exchange-add plan              */
 typedef struct pcgb_solver_s *pcgb_solver_t; /* PCG workspace bound to one operator             */
 typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-by-element operator */
+typedef struct pcgb_asm_s *pcgb_asm_t;     /* device assembly of K_i[Eff,Eff] from the pattern groups (symbolic phase state) */
 typedef struct pcgb_ebe2_s *pcgb_ebe2_t;   /* round-2 preparation: coloured (atomics-free, deterministic) variant */
 
 /* error codes */
@@ -206,6 +207,18 @@ int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream); 
 int64_t pcgb_ebe_bytes(pcgb_ebe_t E);                                            /* algorithmic bytes per application */
 int pcgb_solver_create_ebe(pcgb_ebe_t E, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,
                            pcgb_solver_t *out);
+
+/* ---------------------------------------------------------------- device assembly of the CSR operator (f2)
+ * A_i = K_i[Eff,Eff] = sum_e P_e^T (Ck_e S_e Ke S_e) P_e  from the reference's pattern type groups (partition_mesh.py:443-491;
+ * the operator calcMatVecProd applies element by element, pcg_solver.py:263-300), assembled on the device with hand-written
+ * kernels (csrc/assemble.cuh): incidence lists per dof -> per-row sorted distinct columns (symbolic) -> per-row
+ * accumulation in a fixed element order (numeric).  No atomics in the arithmetic: bit-reproducible.  `groups` uses the same
+ * layout as the EBE operator (d_idx in the free-dof numbering, -1 = clamped).  Two phases because the caller owns the
+ * output arrays: symbolic fills d_rowptr[0..n] (int64) and reports nnz; numeric fills d_col / d_val (ascending columns). */
+int pcgb_assemble_symbolic(int64_t n, int ngroups, const pcgb_ebe_group *groups, int64_t *d_rowptr, int64_t *nnz_out, void *stream,
+                           pcgb_asm_t *out);
+int pcgb_assemble_numeric(pcgb_asm_t a, const int64_t *d_rowptr, int32_t *d_col, double *d_val, void *stream);
+int pcgb_assemble_destroy(pcgb_asm_t a);
 
 /* Round-2 preparation (NOT yet run on hardware, operator-level only, not reachable from pcgb_solve): the same operator
  * with an atomics-free deterministic scatter.  groups[] = one entry per (pattern group, colour) slice, sorted by

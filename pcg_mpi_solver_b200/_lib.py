@@ -88,6 +88,9 @@ SIGNATURES = {
     "pcgb_ebe_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcgb_ebe_bytes": (c_int64, [c_void_p]),
     "pcgb_solver_create_ebe": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "pcgb_assemble_symbolic": (c_int, [c_int64, c_int, POINTER(EbeGroup), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_void_p)]),
+    "pcgb_assemble_numeric": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcgb_assemble_destroy": (c_int, [c_void_p]),
     "pcgb_ebe2_create": (c_int, [c_int64, c_int, POINTER(EbeGroup), POINTER(c_int32), POINTER(c_void_p)]),
     "pcgb_ebe2_destroy": (c_int, [c_void_p]),
     "pcgb_ebe2_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

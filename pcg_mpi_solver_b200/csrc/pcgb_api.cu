@@ -12,6 +12,7 @@
 #include "hexgen.cuh"
 #include "ebe.cuh"
 #include "ebe_color.cuh"
+#include "assemble.cuh"
 
 using namespace pcgb;
 
@@ -22,6 +23,10 @@ struct pcgb_csr_s {
 struct pcgb_ebe_s {
   EbePlan P;
   int device = 0;
+};
+
+struct pcgb_asm_s {
+  AsmPlan P;
 };
 
 struct pcgb_ebe2_s {
@@ -607,6 +612,49 @@ int pcgb_ebe_apply(pcgb_ebe_t E, const double *d_x, double *d_y, void *stream) {
 }
 
 int64_t pcgb_ebe_bytes(pcgb_ebe_t E) { return E ? E->P.bytes : 0; }
+
+// ------------------------------------------------------------------------------------ device assembly (f2)
+int pcgb_assemble_symbolic(int64_t n, int ngroups, const pcgb_ebe_group *groups, int64_t *d_rowptr, int64_t *nnz_out, void *stream,
+                           pcgb_asm_t *out) {
+  if (!out || !d_rowptr || !nnz_out || n < 0 || ngroups < 0 || (ngroups > 0 && !groups)) return fail(PCGB_ERR_ARG, "pcgb_assemble_symbolic: bad argument");
+  if (n >= (1ll << 31) - 8 || ngroups >= 65536) return fail(PCGB_ERR_ARG, "pcgb_assemble_symbolic: too many rows / pattern groups");
+  PCGB_TRY(require_device());
+  pcgb_asm_t a = new pcgb_asm_s();
+  a->P.n = n;
+  int rc = PCGB_OK;
+  for (int g = 0; g < ngroups && rc == PCGB_OK; ++g) {
+    const pcgb_ebe_group &src = groups[g];
+    if (src.nd <= 0 || src.nd > 255 || src.ne < 0 || src.ne >= (1ll << 40) || !src.ke_host || (src.ne > 0 && (!src.d_idx || !src.d_ck))) {
+      rc = fail(PCGB_ERR_ARG, "pcgb_assemble_symbolic: group %d: pattern size must be 1..255 and arrays non-null", g);
+      break;
+    }
+    AsmGroup ag;
+    ag.nd = src.nd; ag.ne = src.ne; ag.idx = src.d_idx; ag.sign = src.d_sign; ag.ck = src.d_ck;
+    double *dke = nullptr;
+    cudaError_t ce = cudaMalloc(&dke, (size_t)src.nd * src.nd * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpy(dke, src.ke_host, (size_t)src.nd * src.nd * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(dke); rc = fail(PCGB_ERR_CUDA, "pcgb_assemble_symbolic: %s", cudaGetErrorString(ce)); break; }
+    ag.ke = dke;
+    a->P.groups.push_back(ag);
+  }
+  if (rc == PCGB_OK) rc = asm_symbolic(a->P, d_rowptr, (cudaStream_t)stream);
+  if (rc != PCGB_OK) { pcgb_assemble_destroy(a); return rc; }
+  *nnz_out = a->P.nnz;
+  *out = a;
+  return PCGB_OK;
+}
+
+int pcgb_assemble_numeric(pcgb_asm_t a, const int64_t *d_rowptr, int32_t *d_col, double *d_val, void *stream) {
+  if (!a || !d_rowptr || (a->P.nnz > 0 && (!d_col || !d_val))) return fail(PCGB_ERR_ARG, "pcgb_assemble_numeric: null argument");
+  return asm_numeric(a->P, d_rowptr, d_col, d_val, (cudaStream_t)stream);
+}
+
+int pcgb_assemble_destroy(pcgb_asm_t a) {
+  if (!a) return PCGB_OK;
+  asm_free(a->P);
+  delete a;
+  return PCGB_OK;
+}
 
 // ------------------------------------------------------------------------------------ coloured EBE operator (round-2 prep)
 // groups[] holds one entry per (pattern group, colour), sorted by colour; phase[g] is the colour.  Pattern matrices of

@@ -214,45 +214,52 @@ def _ebe_matvec(groups, x_full, ndof):
     return y
 
 
-def assemble_csr_device(sub: SubdomainData, device="cuda", chunk_entries: int = 1 << 27):
-    """K_i[Eff,Eff] assembled ON THE DEVICE from the pattern groups: expand to COO keys, stable sort,
-    segmented sum (deterministic), compress to CSR.  Set-up code (torch tensor ops as plumbing; the hot path
-    starts at the CSR arrays).  Returns (rowptr int32/int64, col int32, val float64) CUDA tensors."""
+def assemble_csr_device(sub: SubdomainData, device="cuda"):
+    """K_i[Eff,Eff] assembled ON THE DEVICE from the pattern groups by the library's own kernels (csrc/assemble.cuh through
+    pcgb_assemble_symbolic / pcgb_assemble_numeric): incidence lists per dof, per-row sorted distinct columns, per-row
+    accumulation in a fixed (group, element) order - no atomics in the arithmetic, bit-reproducible, and no nd^2 * N_e
+    COO expansion (a 128^3 METIS part would need ~50 GB that way).  torch only allocates the output arrays.
+    Returns (rowptr int32/int64, col int32, val float64) CUDA tensors."""
+    import ctypes
+
     import torch
+
+    from . import _lib
+    lib = _lib.load()
     n = sub.n
-    eff_map = torch.full((sub.ndof,), -1, dtype=torch.int64, device=device)
-    eff_map[torch.from_numpy(sub.loc_dof_eff).to(device)] = torch.arange(n, device=device)
-    keys, vals = [], []
-    for g in sub.groups:
+    eff_map = np.full(sub.ndof, -1, dtype=np.int32)
+    eff_map[sub.loc_dof_eff] = np.arange(n, dtype=np.int32)
+    keep = []
+    cgroups = (_lib.EbeGroup * max(len(sub.groups), 1))()
+    for k, g in enumerate(sub.groups):
         nd, ne = g.loc_dof.shape
-        ke = torch.from_numpy(g.ke).to(device)
-        step = max(1, chunk_entries // (nd * nd))
-        for e0 in range(0, ne, step):
-            sl = slice(e0, min(ne, e0 + step))
-            r = eff_map[torch.from_numpy(g.loc_dof[:, sl]).to(device)]                       # (nd, m)
-            s = torch.where(torch.from_numpy(g.sign[:, sl]).to(device), -1.0, 1.0).to(torch.float64)
-            ck = torch.from_numpy(g.ck[sl]).to(device)
-            v = (s[:, None, :] * s[None, :, :]) * ke[:, :, None] * ck[None, None, :]          # (nd, nd, m)
-            key = r[:, None, :] * n + r[None, :, :]
-            ok = (r[:, None, :] >= 0) & (r[None, :, :] >= 0)
-            keys.append(key[ok])
-            vals.append(v[ok])
-    key = torch.cat(keys)
-    val = torch.cat(vals)
-    del keys, vals
-    key, perm = torch.sort(key, stable=True)
-    val = val[perm]
-    del perm
-    ukey, counts = torch.unique_consecutive(key, return_counts=True)
-    del key
-    sval = torch.segment_reduce(val, "sum", lengths=counts)
-    rows = ukey // n
-    col = (ukey - rows * n).to(torch.int32)
-    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
-    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
-    if sval.numel() < 2**31:
+        d_idx = torch.from_numpy(np.ascontiguousarray(eff_map[g.loc_dof])).to(device)         # (nd, ne) int32, -1 = clamped
+        d_ck = torch.from_numpy(np.ascontiguousarray(g.ck, dtype=np.float64)).to(device)
+        d_sign = torch.from_numpy(np.ascontiguousarray(g.sign.astype(np.uint8))).to(device) if g.sign.any() else None
+        ke = np.ascontiguousarray(g.ke, dtype=np.float64)
+        keep += [d_idx, d_ck, d_sign, ke]
+        cg = cgroups[k]
+        cg.nd, cg.ne = nd, ne
+        cg.d_idx, cg.d_ck = d_idx.data_ptr(), d_ck.data_ptr()
+        cg.d_sign = d_sign.data_ptr() if d_sign is not None else None
+        cg.ke_host = ke.ctypes.data
+    with torch.cuda.device(device):
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=device)
+        nnz = ctypes.c_int64(0)
+        h = ctypes.c_void_p()
+        _lib.check(lib.pcgb_assemble_symbolic(n, len(sub.groups), cgroups, _lib.ptr(rowptr), ctypes.byref(nnz), _lib.stream_ptr(), ctypes.byref(h)),
+                   "pcgb_assemble_symbolic")
+        try:
+            col = torch.empty(nnz.value, dtype=torch.int32, device=device)
+            val = torch.empty(nnz.value, dtype=torch.float64, device=device)
+            _lib.check(lib.pcgb_assemble_numeric(h, _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.stream_ptr()), "pcgb_assemble_numeric")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            lib.pcgb_assemble_destroy(h)
+    del keep
+    if nnz.value < 2**31:
         rowptr = rowptr.to(torch.int32)
-    return rowptr, col, sval.contiguous()
+    return rowptr, col, val
 
 
 def partition_mesh(model, nparts: int, elepart: np.ndarray | None = None, assemble=True, ncommon: int = 1):
