@@ -980,7 +980,10 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           PCGB_CUDA(cudaStreamSynchronize(st));
           // column-triple index: row-snapped plan, every row offset a multiple of 3, every aligned triple consecutive
           P.t3 = false;
-          if (P.snap && P.nnz % 3 == 0 && P.nnz >= 3 && env_int("PCGB_SPMV_T3", 1) != 0) {
+          // Measured on B200 (profiles/spmv_sweep_r2a.txt, hex 128^3): 1.02 ms with 8 lanes per row against 0.93 ms for the
+          // per-non-zero index - the consumer is bound by shared-memory wavefronts and per-row latency, not by the 13 % fewer HBM
+          // bytes - so the mode is OPT-IN (PCGB_SPMV_T3=1) until the consumer is restructured.
+          if (P.snap && P.nnz % 3 == 0 && P.nnz >= 3 && env_int("PCGB_SPMV_T3", 0) != 0) {
             PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
             k_rows_mod3<RP><<<(int)std::min<int64_t>((P.nrows + 256) / 256, 148 * 8), 256, 0, st>>>(rp, P.nrows, d_fail);
             PCGB_CHECK_LAUNCH();
@@ -1017,7 +1020,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
               cudaFree(P.lidx); P.lidx = nullptr;   // the persistent T3 kernel is the only consumer of the indices
               // lanes per row: a lane owns whole triples; 16 lanes at stride 3 doubles read the values conflict-free
               const double t_avg = avg / 3.0;
-              int l3 = t_avg <= 6.0 ? 4 : t_avg <= 12.0 ? 8 : t_avg <= 40.0 ? 16 : 32;
+              int l3 = t_avg <= 6.0 ? 4 : t_avg <= 40.0 ? 8 : t_avg <= 80.0 ? 16 : 32;   // fewer, fatter row passes win (sweep r2a)
               l3 = env_int("PCGB_SPMV_LANES3", l3);
               if (l3 == 4 || l3 == 8 || l3 == 16 || l3 == 32) P.lanes = l3;
             }

@@ -180,6 +180,7 @@ def test_diag_and_vector_kernels(cuda):
 def test_spmv_triple_index(cuda, monkeypatch, lanes3, tile):
     """Column-triple index: 3 dofs per node make every row a sequence of aligned triples of consecutive columns; the
     persistent kernel then streams ONE 16-bit staged position per triple (8 + 2/3 B per non-zero instead of 10)."""
+    monkeypatch.setenv("PCGB_SPMV_T3", "1")          # opt-in mode (slower than the per-non-zero index on B200 so far)
     monkeypatch.setenv("PCGB_SPMV_LANES3", str(lanes3))
     monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
@@ -200,8 +201,9 @@ def test_spmv_triple_index(cuda, monkeypatch, lanes3, tile):
     assert abs(float(d) - float(x.cpu().numpy() @ y_ref)) <= 1e-12 * float(np.abs(x.cpu().numpy()) @ np.abs(y_ref))
 
 
-def test_spmv_triple_index_not_applicable(cuda):
+def test_spmv_triple_index_not_applicable(cuda, monkeypatch):
     """Rows that are not made of column triples keep the per-non-zero index (Poisson: 27 single columns per row)."""
+    monkeypatch.setenv("PCGB_SPMV_T3", "1")
     M = _check_spmv(R.poisson27(12), cuda)
     assert M.plan_info()["triple_index"] == 0
     # triples by count but not consecutive columns
