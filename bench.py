@@ -524,7 +524,7 @@ def main():
                              "algorithmic_bytes_per_launch": bytes_spmv, "streamed_bytes_per_launch": stream_bytes,
                              "streamed_GBps": stream_bytes / (spmv_ms * 1e-3) / 1e9, "streamed_frac_of_peak": stream_bytes / (spmv_ms * 1e-3) / 1e9 / peak,
                              "mean_launch_ms": spmv_ms, "launches_timed": int(info_k.spmv_timed),
-                             "spmv_share_of_step": spmv_share,
+                             "spmv_share_of_step": spmv_share, "phase_ms_per_iteration": info_k.phase_ms,
                              "iteration": {"algorithmic_bytes": iter_bytes, "achieved_GBps": iter_bytes / (loop_ms / K * 1e-3) / 1e9,
                                            "frac": iter_bytes / (loop_ms / K * 1e-3) / 1e9 / peak}},
                 "parity": parity, "full_solve": full_solve}

@@ -174,6 +174,8 @@ typedef struct pcgb_result {
   int64_t loop_iters; /* iterations executed inside the timed loop                                  */
   double setup_ms;    /* device time from the entry of the solve to the start of the loop (||b||, r0, rho0) */
   double final_ms;    /* device time from the end of the loop to the copy-out of x (finalisation matvec)    */
+  double phase_ms[8]; /* time_kernels: sums over the bracketed iterations of p-update | SpMV | halo pack | p.q reduce+all-reduce |
+                         halo unpack-add | fused update | norms reduce+all-reduce | whole iteration                  */
 } pcgb_result;
 
 int pcgb_solver_create(pcgb_csr_t A, pcgb_halo_t halo /* may be NULL */, pcgb_comm_t comm /* may be NULL */,

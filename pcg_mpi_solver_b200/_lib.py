@@ -32,7 +32,7 @@ class Result(ctypes.Structure):
     _fields_ = [("flag", c_int32), ("iters", c_int32), ("relres", c_double), ("normb", c_double),
                 ("imin", c_int32), ("stag", c_int32), ("moresteps", c_int32), ("too_small_tol", c_int32),
                 ("matvecs", c_int64), ("launches", c_int64), ("loop_ms", c_double), ("spmv_ms", c_double),
-                ("spmv_timed", c_int64), ("loop_iters", c_int64), ("setup_ms", c_double), ("final_ms", c_double)]
+                ("spmv_timed", c_int64), ("loop_iters", c_int64), ("setup_ms", c_double), ("final_ms", c_double), ("phase_ms", c_double * 8)]
 
 
 class EbeGroup(ctypes.Structure):

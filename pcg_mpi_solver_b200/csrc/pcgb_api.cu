@@ -776,7 +776,9 @@ static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pc
     ce = cudaEventCreate(&s->ev_s1);
   if (ce != cudaSuccess) rc = fail(PCGB_ERR_CUDA, "pcgb_solver_create: %s", cudaGetErrorString(ce));
   // interface-first tile order: the tiles owning exchanged rows run first, their values travel while the rest computes
-  if (rc == PCGB_OK && A && halo && halo->ndof > 0 && env_int("PCGB_OVERLAP", 1) != 0)
+  // Opt-in (PCGB_OVERLAP=1): with the peer-store halo the exchange costs a few microseconds and is not worth a second
+  // persistent launch (B200 x2, 128^3 per GPU: 1.118 ms/iteration split against 1.106 ms unsplit, profiles/bench_r2b_*).
+  if (rc == PCGB_OK && A && halo && halo->ndof > 0 && env_int("PCGB_OVERLAP", 0) != 0)
     rc = spmv_set_boundary_rows(A->P, halo->d_dof, halo->ndof, s->own);
   if (rc != PCGB_OK) { pcgb_solver_destroy(s); return rc; }
   *out = s;
@@ -875,16 +877,22 @@ int rz_to_device(pcgb_solver_t s, const double *minv, const double *w, cudaStrea
 }
 
 // one PCG iteration enqueued on st (pcg_solver.py:438-562); every kernel no-ops once the state is frozen.
-// ev[0..4): optional event brackets around the SpMV launch(es) of this iteration (time_kernels).
+// ev[0..kEvPerIter): optional events at the phase boundaries of this iteration (time_kernels):
+//   0 start | 1 after p-update | 2 after SpMV (interface tiles when split) | 3 after halo pack | 4 after the interior tiles |
+//   5 after the p.q reduction + all-reduce + alpha | 6 after halo unpack-add | 7 after the fused update | 8 after the norms reduction
+constexpr int kEvPerIter = 9;
 int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, double *xb0, double *resvec, cudaStream_t st, int *nl,
                       cudaEvent_t *ev = nullptr) {
   const int64_t n = s->n;
   const int vg = vec_grid(n);
   const bool multi = multi_rank(s);
   const bool peer = peer_path(s);
+#define PCGB_MARK(k) do { if (ev) PCGB_CUDA(cudaEventRecord(ev[k], st)); } while (0)
+  PCGB_MARK(0);
   k_pupdate<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, minv, s->p);
   PCGB_CHECK_LAUNCH();
   *nl += 1;
+  PCGB_MARK(1);
   // p.q : per-tile partials -> (stage) -> scalar.  In the multi-GPU case the partials are those of the
   // UNASSEMBLED local product, whose rank sum equals the reference's weighted dot of the assembled q
   // (p is consistent on shared dofs and K = sum of the subdomain matrices); see DESIGN.md.
@@ -892,9 +900,8 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
   int pq_cnt;
   bool halo_done = false;
   if (s->E) {  // matrix-free operator: product, then a separate unweighted dot of the local product
-    if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
     PCGB_TRY(ebe_apply(s->E->P, s->p, s->q, st, nl, &s->d_ctrl->state));
-    if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
+    PCGB_MARK(2); PCGB_MARK(3); PCGB_MARK(4);
     k_dot_w<<<vg, kVecBlock, 0, st>>>(n, s->p, s->q, nullptr, s->partials);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
@@ -903,19 +910,19 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
     const CsrPlan &P = s->A->P;
     if (peer && s->halo && s->halo->m > 0 && spmv_split_available(P)) {
       // interface tiles -> pack (peer stores fly over NVLink) -> interior tiles; the unpack follows the p.q all-reduce
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
       PCGB_TRY(spmv_launch_part(P, 0, s->p, s->q, true, st, nl, &s->d_ctrl->state));
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
+      PCGB_MARK(2);
       PCGB_TRY(halo_pack(s->halo, s->q, st, nl));
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[2], st));
+      PCGB_MARK(3);
       PCGB_TRY(spmv_launch_part(P, 1, s->p, s->q, true, st, nl, &s->d_ctrl->state));
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[3], st));
+      PCGB_MARK(4);
       pq_src = P.dot_partials_split; pq_cnt = spmv_split_dot_count(P);
       halo_done = true;
     } else {
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[0], st));
       PCGB_TRY(spmv_launch(P, s->p, s->q, true, st, nl, &s->d_ctrl->state));
-      if (ev) PCGB_CUDA(cudaEventRecord(ev[1], st));
+      PCGB_MARK(2);
+      if (peer && s->halo) { PCGB_TRY(halo_pack(s->halo, s->q, st, nl)); halo_done = true; }
+      PCGB_MARK(3); PCGB_MARK(4);
       pq_src = P.dot_partials;
       pq_cnt = P.persist ? P.grid_persist : P.ntiles;
       if (pq_cnt > 8192) {
@@ -934,30 +941,39 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
     k_reduce_ar<1, 1><<<1, 256, 0, st>>>(win, s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
+    PCGB_MARK(5);
     if (s->halo) PCGB_TRY(halo_unpack(s->halo, s->q, st, nl));
+    PCGB_MARK(6);
     k_update<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, s->q, s->p, minv, w, xb0, s->xalt, s->partials);
     PCGB_CHECK_LAUNCH();
+    PCGB_MARK(7);
     k_reduce_ar<5, 2><<<1, 256, 0, st>>>(win, s->d_ctrl, s->partials, vg, kMaxVecGrid, s->red + 1, resvec);
     PCGB_CHECK_LAUNCH();
     *nl += 2;
+    PCGB_MARK(8);
     return PCGB_OK;
   }
-  if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
   if (!multi) {
     k_reduce<1, 1><<<1, 256, 0, st>>>(s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
+    PCGB_MARK(5); PCGB_MARK(6);
   } else {
+    // NCCL transport: reduction, ncclAllReduce and the scalar logic are three stream operations; the halo is serial
     k_reduce<1, 0><<<1, 256, 0, st>>>(s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();
     PCGB_TRY(allreduce_sum(s->comm, s->red, 1, st));
     k_ctrl_alpha<<<1, 1, 0, st>>>(s->d_ctrl, s->red);
     PCGB_CHECK_LAUNCH();
     *nl += 2;
+    PCGB_MARK(5);
+    if (s->halo) PCGB_TRY(halo_exchange_add(s->halo, s->q, st, nl));
+    PCGB_MARK(6);
   }
   k_update<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, s->q, s->p, minv, w, xb0, s->xalt, s->partials);
   PCGB_CHECK_LAUNCH();
   *nl += 1;
+  PCGB_MARK(7);
   if (!multi) {
     k_reduce<5, 2><<<1, 256, 0, st>>>(s->d_ctrl, s->partials, vg, kMaxVecGrid, s->red + 1, resvec);
     PCGB_CHECK_LAUNCH();
@@ -970,6 +986,8 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
     PCGB_CHECK_LAUNCH();
     *nl += 2;
   }
+  PCGB_MARK(8);
+#undef PCGB_MARK
   return PCGB_OK;
 }
 
@@ -1083,7 +1101,6 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   if (batch > opt->maxiter) batch = opt->maxiter;
   const bool want_graph = opt->use_graph != 0 && !opt->time_kernels;
   size_t ktimed = 0;           // iterations whose SpMV launches carry event brackets
-  int ev_per_iter = 2;
   PCGB_CUDA(cudaEventRecord(s->ev_l0, st));
   int flag = 1;
   int too_small = 0;
@@ -1109,14 +1126,12 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
       PCGB_CUDA(cudaGraphLaunch(s->gexec, st));
       graph_launch_kernels += (int64_t)s->launches_per_iter * batch;
     } else {
-      const bool split = !s->E && peer_path(s) && s->halo && s->halo->m > 0 && spmv_split_available(s->A->P);
-      ev_per_iter = split ? 4 : 2;
       for (int k = 0; k < batch; ++k) {
         int nl = 0;
         cudaEvent_t *ev = nullptr;
         if (opt->time_kernels && ktimed < 1024) {
-          while (s->ev_k.size() < 4 * (ktimed + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
-          ev = &s->ev_k[4 * ktimed]; ++ktimed;
+          while (s->ev_k.size() < (size_t)kEvPerIter * (ktimed + 1)) { cudaEvent_t e; PCGB_CUDA(cudaEventCreate(&e)); s->ev_k.push_back(e); }
+          ev = &s->ev_k[(size_t)kEvPerIter * ktimed]; ++ktimed;
         }
         PCGB_TRY(enqueue_iteration(s, d_minv, d_w, xw, d_resvec, st, &nl, ev));
         s->launches += nl;
@@ -1186,13 +1201,23 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
     res->setup_ms = ms;
     PCGB_CUDA(cudaEventElapsedTime(&ms, s->ev_l1, s->ev_s1));
     res->final_ms = ms;
+    // phase sums over the bracketed iterations: p-update | SpMV | halo pack | p.q reduce + all-reduce | halo unpack |
+    // fused update | norms reduce + all-reduce   (phase_ms[7] = their total)
     double tot = 0.0;
-    for (size_t k = 0; k < ktimed; ++k)
-      for (int e = 0; e + 1 < ev_per_iter; e += 2) {
-        float t = 0.f;
-        PCGB_CUDA(cudaEventElapsedTime(&t, s->ev_k[4 * k + e], s->ev_k[4 * k + e + 1]));
-        tot += t;
+    static const int seg[7][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}, {5, 6}, {6, 7}, {7, 8}};
+    for (size_t k = 0; k < ktimed; ++k) {
+      const cudaEvent_t *e = &s->ev_k[(size_t)kEvPerIter * k];
+      float t = 0.f;
+      for (int ph = 0; ph < 7; ++ph) {
+        PCGB_CUDA(cudaEventElapsedTime(&t, e[seg[ph][0]], e[seg[ph][1]]));
+        res->phase_ms[ph] += t;
       }
+      PCGB_CUDA(cudaEventElapsedTime(&t, e[3], e[4]));   // interior tiles of a split SpMV (zero-length otherwise)
+      res->phase_ms[1] += t;
+      PCGB_CUDA(cudaEventElapsedTime(&t, e[0], e[8]));
+      res->phase_ms[7] += t;
+    }
+    tot = res->phase_ms[1];
     res->spmv_ms = tot; res->spmv_timed = (int64_t)ktimed;
   }
   res->flag = flag; res->iters = iter_out; res->relres = relres; res->imin = c.imin; res->stag = c.stag;

@@ -149,6 +149,7 @@ class SolveInfo:
     loop_iters: int = 0
     setup_ms: float = 0.0
     final_ms: float = 0.0
+    phase_ms: dict | None = None
     resvec: np.ndarray | None = None
 
 
@@ -242,6 +243,9 @@ class SubdomainOperator:
         info = SolveInfo(res.flag, res.iters, res.relres, res.normb, res.imin, res.stag, res.moresteps,
                          bool(res.too_small_tol), res.matvecs, res.launches, res.loop_ms, res.spmv_ms,
                          res.spmv_timed, res.loop_iters, res.setup_ms, res.final_ms)
+        if time_kernels and res.spmv_timed > 0:
+            names = ["p_update", "spmv", "halo_pack", "pq_reduce_allreduce", "halo_unpack", "fused_update", "norms_reduce_allreduce", "iteration"]
+            info.phase_ms = {k: res.phase_ms[i] / res.spmv_timed for i, k in enumerate(names)}
         if record_resvec:
             info.resvec = resvec[: int(res.loop_iters) + 1].cpu().numpy()   # ||r_0|| .. ||r_k||, k = iterations executed
         return x, info
