@@ -78,8 +78,9 @@ class CsrMatrix:
     def plan_info(self) -> dict:
         info = (ctypes.c_int64 * 16)()
         _lib.check(_lib.load().pcgb_csr_plan_info(self._h, info))
+        # index_mode: 0 = one 16-bit staged position (or 32-bit column) per non-zero, 1 = per column triple, 2 = per 3x3 node block
         keys = ["ntiles", "tile_items", "lanes", "snap", "split_rows", "smem_bytes", "max_row", "tma", "staged", "x_windows",
-                "x_cap", "max_windows_per_tile", "triple_index", "interface_tiles", "resident_ctas", "col_released"]
+                "x_cap", "max_windows_per_tile", "index_mode", "interface_tiles", "resident_ctas", "col_released"]
         return dict(zip(keys, [int(v) for v in info]))
 
     def release_col(self) -> bool:

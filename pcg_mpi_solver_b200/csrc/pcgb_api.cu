@@ -221,7 +221,7 @@ int64_t pcgb_spmv_bytes(pcgb_csr_t A) {
 int64_t pcgb_spmv_stream_bytes(pcgb_csr_t A) {
   if (!A) return 0;
   const CsrPlan &P = A->P;
-  const int64_t idx_bytes = (P.persist && P.t3) ? (2 * P.nnz) / 3 : (P.staged ? 2 * P.nnz : 4 * P.nnz);
+  const int64_t idx_bytes = P.bsr ? (2 * P.nnz) / 9 : (P.persist && P.t3) ? (2 * P.nnz) / 3 : (P.staged ? 2 * P.nnz : 4 * P.nnz);
   return 8 * P.nnz + idx_bytes + (P.rp64 ? 8 : 4) * (P.nrows + 1) + 8 * P.ncols + 8 * P.nrows +
          (P.staged ? 8 * P.nwin + 8 * (int64_t)P.ntiles : 0) + (P.persist ? 32 : 12) * (int64_t)P.ntiles;
 }
@@ -233,7 +233,7 @@ int pcgb_csr_plan_info(pcgb_csr_t A, int64_t info[16]) {
   info[4] = P.nfix; info[5] = P.staged ? P.smem_staged : P.smem_bytes; info[6] = P.max_row; info[7] = P.use_tma ? 1 : 0;
   info[8] = P.persist ? 2 : (P.staged ? 1 : 0); info[9] = P.nwin; info[10] = P.cap_x; info[11] = P.max_nw;
   if (P.persist) info[5] = P.smem_persist;
-  info[12] = P.t3 ? 1 : 0; info[13] = P.desc_split ? P.nb_tiles : -1; info[14] = P.persist ? P.grid_persist : 0; info[15] = P.col ? 0 : 1;
+  info[12] = P.bsr ? 2 : (P.t3 ? 1 : 0); info[13] = P.desc_split ? P.nb_tiles : -1; info[14] = P.persist ? P.grid_persist : 0; info[15] = P.col ? 0 : 1;
   return PCGB_OK;
 }
 

@@ -72,6 +72,12 @@ struct CsrPlan {
   // (3 dofs per node: hex / concrete), ONE 16-bit index is stored per triple -> 8 + 2/3 bytes per non-zero
   bool t3 = false;
   uint16_t *lidx3 = nullptr;       // [nnz/3 + 16]
+  // node-block mode ("BSR-3"): 3 dofs per node give rows 3n, 3n+1, 3n+2 the SAME column pattern made of aligned column
+  // triples; one thread then owns a whole 3x3 block (9 values, 3 x entries, ONE 16-bit staged position): 8 + 2/9 bytes per
+  // non-zero from HBM, a third of the x gathers and a ninth of the index loads of the row-group consumer
+  bool bsr = false;
+  uint16_t *bidx = nullptr;        // [nnz/9 + 16]  staged x position of block t of node n at rowptr[3n]/9 + t
+  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0;
   // interface-first split (multi-GPU overlap): tiles that own an interface row are listed first in desc_split
   struct TileDesc *desc_split = nullptr;  // [ntiles] permutation of tile_desc
   int nb_tiles = 0;                       // leading boundary tiles of desc_split
@@ -148,7 +154,7 @@ __device__ __forceinline__ int64_t merge_path_rows(const RP *__restrict__ rowptr
 
 template <typename RP>
 __global__ void k_partition(const RP *__restrict__ rowptr, int64_t nrows, int64_t nnz, int tile_items, int ntiles, int snap,
-                            int *tile_row, int64_t *tile_k) {
+                            int *tile_row, int64_t *tile_k, int snap_unit = 1) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > ntiles) return;
   int64_t total = nrows + nnz;
@@ -156,7 +162,10 @@ __global__ void k_partition(const RP *__restrict__ rowptr, int64_t nrows, int64_
   if (d > total || b == ntiles) d = total;
   int64_t i = merge_path_rows(rowptr, nrows, nnz, d);
   int64_t j = d - i;
-  if (snap) j = (int64_t)rowptr[i];
+  if (snap) {
+    if (i < nrows) i -= i % snap_unit;   // node-block mode: tiles start at a node (3 rows), never inside one
+    j = (int64_t)rowptr[i];
+  }
   tile_row[b] = (int)i;
   tile_k[b] = j;
 }
@@ -767,6 +776,227 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
   }
 }
 
+// ------------------------------------------------------------------ node-block ("BSR-3") persistent kernel
+// Same tiles, x windows, TMA / mbarrier ring and producer warps as k_spmv_persist; the CONSUMER differs: the tile is a
+// whole number of nodes (3 rows with one column pattern of aligned triples) and is processed as a flat list of 3x3 blocks,
+// one block per consumer thread per pass:
+//     phase 1   thread b: node i by binary search in the node offsets, ONE 16-bit staged position -> x triple (3 LDS),
+//               9 values at stride 3 doubles across the lanes (conflict-free), 9 FMAs -> 3 row partials to shared memory;
+//     phase 2   (after one named barrier, scratch double-buffered by tile parity) thread r < R adds the partials of its
+//               row in block order -> y[r]: fixed summation order, bit-reproducible, no shuffles, no atomics.
+// Per 9 non-zeros: 13 shared-memory loads + 3 stores instead of 27 loads, and 8 + 2/9 bytes from HBM instead of 10.
+template <bool DOT, typename RP>
+__global__ void __launch_bounds__((kConsWarps + 4) * 32)
+k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, const double *__restrict__ val,
+            const double *__restrict__ x, double *__restrict__ y, const TileDesc *__restrict__ desc,
+            const int *__restrict__ win_start, const int *__restrict__ win_off, int ntiles, int64_t nnz, int cap_nnz,
+            int cap_nodes, int cap_x, int cap_blocks, int stages, int stage_bytes, double *__restrict__ dot_partials,
+            const int *__restrict__ skip) {
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8];
+  __shared__ double red[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nprod = (int)(blockDim.x >> 5) - kConsWarps;   // producer warps; stages % nprod == 0
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 34); mbar_init(&empty_bar[s], kConsWarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | snp[cap_nodes+2] i64 | sbidx[cap_blocks+16] u16 | meta[8] i32
+  const size_t off_sx = (size_t)cap_nnz * 8, off_snp = off_sx + (size_t)cap_x * 8;
+  const size_t off_sb = off_snp + (size_t)(cap_nodes + 2) * 8, off_meta = (off_sb + (size_t)(cap_blocks + 16) * 2 + 15) & ~(size_t)15;
+  // scratch behind the stages: row partials [2][3*cap_blocks] f64, node block offsets [2][cap_nodes+2] i32
+  double *spart = reinterpret_cast<double *>(smem_raw + (size_t)stages * stage_bytes);
+  int *snbo = reinterpret_cast<int *>(spart + (size_t)6 * cap_blocks);
+
+  if (warp >= kConsWarps) {
+    // ================= producer warp p (see k_spmv_persist): TMA val + block indices, cp.async node offsets + x windows
+    const int p = warp - kConsWarps;
+    const uint64_t pol = l2_evict_first_policy();
+    int it = p;
+    int tile = blockIdx.x + it * gridDim.x;
+    bool have = tile < ntiles;
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = make_int4(0, 0, 0, 0);
+    int ws = 0, wo = 0;
+    if (have) {
+      const int4 *dp = reinterpret_cast<const int4 *>(desc + tile);
+      d0 = __ldg(dp); d1 = __ldg(dp + 1);
+      if (lane < d1.z) { ws = __ldg(win_start + d1.y + lane); wo = __ldg(win_off + d1.y + lane); }
+    }
+    while (have) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)((it / stages) & 1);
+      const int nit = it + nprod;
+      const int ntile = blockIdx.x + nit * gridDim.x;
+      const bool nhave = ntile < ntiles;
+      int4 nd0 = make_int4(0, 0, 0, 0), nd1 = make_int4(0, 0, 0, 0);
+      if (nhave) {
+        const int4 *dp = reinterpret_cast<const int4 *>(desc + ntile);
+        nd0 = __ldg(dp); nd1 = __ldg(dp + 1);
+      }
+      const int64_t k0 = ((int64_t)(uint32_t)d0.x) | ((int64_t)d0.y << 32);
+      const int cnt = d0.z, r0 = d0.w, R = d1.x & 0x7fffffff, wb = d1.y, nw = d1.z, xlen = d1.w;
+      unsigned char *base = smem_raw + (size_t)s * stage_bytes;
+      double *sval = reinterpret_cast<double *>(base);
+      double *sx = reinterpret_cast<double *>(base + off_sx);
+      RP *snp = reinterpret_cast<RP *>(base + off_snp);
+      uint16_t *sb = reinterpret_cast<uint16_t *>(base + off_sb);
+      int *meta = reinterpret_cast<int *>(base + off_meta);
+      const int64_t k1 = k0 + cnt;
+      const int64_t ka = k0 & ~(int64_t)kAlignMask;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (lane == 0) {
+        int64_t kend = (k1 + kAlignMask) & ~(int64_t)kAlignMask;
+        const int64_t lim = nnz & ~(int64_t)kAlignMask;
+        if (kend > lim) kend = lim;
+        const int nb = (int)(kend - ka);
+        // bidx is padded by 16 entries: the aligned window [ba, bend) never leaves the array
+        const int64_t b0 = k0 / 9, ba = b0 & ~(int64_t)kAlignMask;
+        const int64_t bend = (b0 + cnt / 9 + kAlignMask) & ~(int64_t)kAlignMask;
+        const uint32_t ib = (uint32_t)(bend - ba) * 2u;
+        mbar_expect_tx(&full_bar[s], (nb > 0 ? (uint32_t)nb * 8u : 0u) + ib);
+        if (nb > 0) bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &full_bar[s], pol);
+        if (ib > 0) bulk_g2s(sb, bidx + ba, ib, &full_bar[s], pol);
+        meta[0] = r0; meta[1] = R; meta[2] = tile; meta[3] = cnt;
+        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32); meta[6] = (int)(b0 - ba);
+      }
+      {
+        const int64_t lim = nnz & ~(int64_t)kAlignMask;
+        const int64_t kt = (lim > ka ? lim : ka) + lane;
+        if (lane <= kAlignMask && kt >= lim && kt < k1) sval[kt - ka] = val[kt];
+      }
+      // offsets of the first row of every node of the tile (+ the end): asynchronous copies
+      for (int i = lane; i <= R / 3; i += 32) cp_async<sizeof(RP)>(snp + i, rowptr + r0 + 3 * i);
+      for (int w0 = 0; w0 < nw; w0 += 32) {
+        if (w0 > 0) {
+          ws = 0; wo = 0;
+          if (w0 + lane < nw) { ws = __ldg(win_start + wb + w0 + lane); wo = __ldg(win_off + wb + w0 + lane); }
+        }
+        const int nwc = min(32, nw - w0);
+        const int wo_next = (w0 + nwc < nw) ? __ldg(win_off + wb + w0 + nwc) : xlen;
+        for (int w = 0; w < nwc; ++w) {
+          const int s0 = __shfl_sync(0xffffffffu, ws, w), o0 = __shfl_sync(0xffffffffu, wo, w);
+          const int o1n = __shfl_sync(0xffffffffu, wo, (w + 1) & 31);
+          const int len = ((w + 1 < nwc) ? o1n : wo_next) - o0;
+          for (int t = lane; t < len; t += 32) cp_async<8>(sx + o0 + t, x + s0 + t);
+        }
+      }
+      int nws = 0, nwo = 0;
+      if (nhave && lane < nd1.z) { nws = __ldg(win_start + nd1.y + lane); nwo = __ldg(win_off + nd1.y + lane); }
+      cp_async_arrive_noinc(&full_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      d0 = nd0; d1 = nd1; ws = nws; wo = nwo; it = nit; tile = ntile; have = nhave;
+    }
+    return;
+  }
+
+  // ================= consumer warps (kConsWarps * 32 threads, tid = consumer thread id)
+  constexpr int NT = kConsWarps * 32;
+  double dsum = 0.0;
+  for (int it = 0;; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) break;
+    const int s = it % stages;
+    const uint32_t ph = (uint32_t)((it / stages) & 1);
+    const int par = it & 1;
+    const unsigned char *base = smem_raw + (size_t)s * stage_bytes;
+    const double *sval = reinterpret_cast<const double *>(base);
+    const double *sx = reinterpret_cast<const double *>(base + off_sx);
+    const RP *snp = reinterpret_cast<const RP *>(base + off_snp);
+    const uint16_t *sb = reinterpret_cast<const uint16_t *>(base + off_sb);
+    const int *meta = reinterpret_cast<const int *>(base + off_meta);
+    double *part = spart + (size_t)par * 3 * cap_blocks;
+    int *nbo = snbo + par * (cap_nodes + 2);
+    mbar_wait(&full_bar[s], ph);
+    const int r0 = meta[0], R = meta[1], cnt = meta[3];
+    const int64_t k0 = ((int64_t)(uint32_t)meta[4]) | ((int64_t)meta[5] << 32);
+    const int k0l = (int)(k0 & kAlignMask);
+    const int NN = R / 3, NB = cnt / 9;
+    const uint16_t *sbt = sb + meta[6];
+    const double *svt = sval + k0l;
+    // block offset of every node (kept for phase 2, which runs after the stage has been handed back)
+    for (int i = tid; i <= NN; i += NT) nbo[i] = (int)((int64_t)snp[i] - k0) / 9;
+    // ---- phase 1: one 3x3 block per thread and pass
+    for (int b = tid; b < NB; b += NT) {
+      int lo = 0, hi = NN - 1;                     // node of block b: last i with (snp[i] - k0) <= 9 b
+      const int kb = 9 * b;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)((int64_t)snp[mid] - k0) <= kb) lo = mid; else hi = mid - 1;
+      }
+      const int noff = (int)((int64_t)snp[lo] - k0);
+      const int L = ((int)((int64_t)snp[lo + 1] - k0) - noff) / 3;   // non-zeros per row of this node
+      const int ii = sbt[b];
+      const double *pv = svt + noff + (kb - noff) / 3;                 // 3 t, t = b - noff / 9
+      const double x0 = sx[ii], x1 = sx[ii + 1], x2 = sx[ii + 2];
+      const double p0 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
+      pv += L;
+      const double p1 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
+      pv += L;
+      const double p2 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
+      double *pp = part + 3 * b;
+      pp[0] = p0; pp[1] = p1; pp[2] = p2;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);     // the stage is free: everything phase 2 needs is in the scratch
+    named_bar_sync(1, NT);
+    // ---- phase 2: one row per thread, partials added in block order
+    for (int r = tid; r < R; r += NT) {
+      const int i = r / 3, k = r - 3 * i;
+      const int b0 = nbo[i], b1 = nbo[i + 1];
+      double acc = 0.0;
+      for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
+      y[r0 + r] = acc;
+      if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
+    }
+  }
+  if (DOT) {
+    double v = warp_sum(dsum);
+    if (lane == 0) red[warp] = v;
+    named_bar_sync(1, NT);
+    if (warp == 0) {
+      double t = lane < kConsWarps ? red[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) dot_partials[blockIdx.x] = t;
+    }
+  }
+}
+
+// ---- node-block plan helpers
+// eligibility: rows 3n, 3n+1, 3n+2 have one length (a multiple of 3) and one column pattern made of aligned consecutive triples
+template <typename RP>
+__global__ void k_check_bsr3(const RP *__restrict__ rowptr, const int *__restrict__ col, int64_t nnodes, int *__restrict__ fail) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a0 = rowptr[3 * n], a1 = rowptr[3 * n + 1], a2 = rowptr[3 * n + 2], a3 = rowptr[3 * n + 3];
+    const int64_t L = a1 - a0;
+    if (a2 - a1 != L || a3 - a2 != L || L % 3 != 0) { *fail = 1; return; }
+    for (int64_t t = 0; t < L; t += 3) {
+      const int c = col[a0 + t];
+      if (col[a0 + t + 1] != c + 1 || col[a0 + t + 2] != c + 2) { *fail = 1; return; }
+      if (col[a1 + t] != c || col[a2 + t] != c || col[a1 + t + 1] != c + 1 || col[a1 + t + 2] != c + 2 ||
+          col[a2 + t + 1] != c + 1 || col[a2 + t + 2] != c + 2) { *fail = 1; return; }
+    }
+  }
+}
+// one 16-bit staged position per 3x3 block from the per-non-zero positions of the same tiles (rows of a node agree)
+template <typename RP>
+__global__ void k_build_bidx(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx, int64_t nnodes,
+                             uint16_t *__restrict__ bidx, int *__restrict__ fail) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a0 = rowptr[3 * n], a1 = rowptr[3 * n + 1], a2 = rowptr[3 * n + 2];
+    const int64_t L = a1 - a0;
+    for (int64_t t = 0; t < L; t += 3) {
+      const unsigned p = lidx[a0 + t];
+      if (lidx[a0 + t + 1] != p + 1 || lidx[a0 + t + 2] != p + 2 || lidx[a1 + t] != p || lidx[a2 + t] != p) *fail = 1;
+      bidx[a0 / 9 + t / 3] = (uint16_t)p;   // a0 % 9 == 0: blocks before node n = rowptr[3n] / 9
+    }
+  }
+}
+
 // ---- T3 plan helpers
 // every row offset a multiple of 3  <=>  every row length a multiple of 3 (rowptr[0] = 0)
 template <typename RP>
@@ -869,10 +1099,31 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   }
   if (P.tile_items < 256) P.tile_items = 256;
   P.lanes = lanes;
-  P.snap = P.max_row <= P.tile_items / 4 && env_int("PCGB_SPMV_SNAP", 1) != 0;
   P.use_tma = env_int("PCGB_SPMV_TMA", 1) != 0;
   // TMA bulk copies need 16-byte aligned global sources
   if ((reinterpret_cast<uintptr_t>(P.val) & 15) || (reinterpret_cast<uintptr_t>(P.col) & 15)) P.use_tma = false;
+  // node-block mode: is this a 3-dofs-per-node matrix (rows 3n..3n+2 share one pattern of aligned column triples)?
+  bool bsr_ok = false;
+  if (P.use_tma && P.nrows > 0 && P.nrows % 3 == 0 && P.nnz % 9 == 0 && P.nnz > 0 && env_int("PCGB_SPMV_BSR", 1) != 0 &&
+      env_int("PCGB_SPMV_STAGE", 1) != 0 && env_int("PCGB_SPMV_PERSIST", 1) != 0 && env_int("PCGB_SPMV_SNAP", 1) != 0) {
+    PCGB_CUDA(cudaMemsetAsync(d_stats + 3, 0, sizeof(int), st));
+    k_check_bsr3<RP><<<(int)std::min<int64_t>((P.nrows / 3 + 127) / 128, 148 * 16), 128, 0, st>>>(rp, P.col, P.nrows / 3, d_stats + 3);
+    PCGB_CHECK_LAUNCH();
+    PCGB_CUDA(cudaMemcpyAsync(h_stats + 3, d_stats + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCGB_CUDA(cudaStreamSynchronize(st));
+    bsr_ok = h_stats[3] == 0;
+    h_stats[3] = 0;
+  }
+  if (bsr_ok) {
+    // one 3x3 block per consumer thread and pass (256 threads): a tile of at most 256 (or 512) blocks whatever the node snap does
+    const int node_items = 3 * (P.max_row + 1);
+    int t = 2304 - node_items;
+    if (t < 1536) t = 4608 - node_items;
+    if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
+    else P.tile_items = env_int("PCGB_SPMV_TILE", t);
+    if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
+  }
+  P.snap = bsr_ok || (P.max_row <= P.tile_items / 4 && env_int("PCGB_SPMV_SNAP", 1) != 0);
 
   const int64_t total = P.nrows + P.nnz;
   int64_t nt = (total + P.tile_items - 1) / P.tile_items;
@@ -887,7 +1138,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   unsigned char *d_head = nullptr;
   PCGB_CUDA(cudaMalloc(&d_head, (size_t)P.ntiles));
   k_partition<RP><<<(P.ntiles + 1 + 255) / 256, 256, 0, st>>>(rp, P.nrows, P.nnz, P.tile_items, P.ntiles, P.snap ? 1 : 0,
-                                                               P.tile_row, P.tile_k);
+                                                               P.tile_row, P.tile_k, bsr_ok ? 3 : 1);
   PCGB_CHECK_LAUNCH();
   k_tile_stats<RP><<<(P.ntiles + 255) / 256, 256, 0, st>>>(rp, P.tile_row, P.tile_k, P.ntiles, d_stats + 1, d_stats + 2, d_head);
   PCGB_CHECK_LAUNCH();
@@ -1014,9 +1265,52 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           if (fit < 1) fit = 1;
           P.ctas_per_sm = std::min(ctas > 0 ? ctas : 1, fit);
           P.grid_persist = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
+          if (P.persist && bsr_ok) {
+            // node-block index stream from the per-non-zero positions of the same (node-aligned) tiles
+            PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+            const int64_t nblk = P.nnz / 9;
+            PCGB_CUDA(cudaMalloc(&P.bidx, ((size_t)nblk + 16) * sizeof(uint16_t)));
+            PCGB_CUDA(cudaMemsetAsync(P.bidx + nblk, 0, 16 * sizeof(uint16_t), st));
+            k_build_bidx<RP><<<(int)std::min<int64_t>((P.nrows / 3 + 127) / 128, 148 * 16), 128, 0, st>>>(rp, P.lidx, P.nrows / 3, P.bidx, d_fail);
+            PCGB_CHECK_LAUNCH();
+            int h_fb = 1;
+            PCGB_CUDA(cudaMemcpyAsync(&h_fb, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PCGB_CUDA(cudaStreamSynchronize(st));
+            P.cap_blocks = (P.cap_nnz / 9 + 2 + 7) & ~7;
+            P.cap_nodes = (P.cap_rows / 3 + 2 + 1) & ~1;
+            P.bsr_stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + (P.cap_nodes + 2) * 8 + (((P.cap_blocks + 16) * 2 + 15) & ~15) + 32;
+            P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
+            const int scratch = 6 * P.cap_blocks * 8 + 2 * (P.cap_nodes + 2) * 4;
+            // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
+            int bst = 4, bct = 2;
+            if (2 * (4 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) {
+              if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) <= 227 * 1024) bst = 2;
+              else bct = 1;
+            }
+            bst = env_int("PCGB_SPMV_STAGES", bst);
+            bct = env_int("PCGB_SPMV_CTAS", bct);
+            if (bst < 1) bst = 1;
+            if (bst > 8) bst = 8;
+            P.bsr_prod = bst >= 4 ? 4 : bst;                 // producer warps; stages % producers == 0
+            bst -= bst % P.bsr_prod;
+            P.bsr_stages = bst;
+            P.smem_bsr = bst * P.bsr_stage_bytes + scratch;
+            int bfit = (227 * 1024) / (P.smem_bsr + 2048);
+            if (bfit < 1) bfit = 1;
+            P.bsr = h_fb == 0 && P.smem_bsr <= 200 * 1024;
+            if (P.bsr) {
+              P.ctas_per_sm = std::min(bct > 0 ? bct : 1, bfit);
+              P.grid_bsr = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
+              P.grid_persist = P.grid_bsr; P.smem_persist = P.smem_bsr; P.stages = P.bsr_stages; P.stage_bytes = P.bsr_stage_bytes;
+              cudaFree(P.lidx); P.lidx = nullptr;           // the node-block kernel is the only consumer of the index stream now
+              if (P.t3) { cudaFree(P.lidx3); P.lidx3 = nullptr; P.t3 = false; }
+            } else {
+              cudaFree(P.bidx); P.bidx = nullptr;
+            }
+          }
           if (P.persist) {
             PCGB_CUDA(cudaMalloc(&P.dot_partials_split, (size_t)2 * (size_t)std::max(P.grid_persist, 1) * sizeof(double)));
-            if (P.t3) {
+            if (P.t3 && !P.bsr) {
               cudaFree(P.lidx); P.lidx = nullptr;   // the persistent T3 kernel is the only consumer of the indices
               // lanes per row: a lane owns whole triples; 16 lanes at stride 3 doubles read the values conflict-free
               const double t_avg = avg / 3.0;
@@ -1027,6 +1321,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           } else if (P.t3) {
             cudaFree(P.lidx3); P.lidx3 = nullptr; P.t3 = false;
           }
+          if (!P.persist && P.bidx) { cudaFree(P.bidx); P.bidx = nullptr; P.bsr = false; }
         }
       }
     }
@@ -1120,9 +1415,31 @@ inline int launch_persist_lanes(const CsrPlan &P, const double *x, double *y, cu
   }
 }
 
+template <bool DOT, typename RP>
+inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
+                           int ntiles, int grid, double *dotp) {
+  auto kern = k_spmv_bsr3<DOT, RP>;
+  if (skip == reinterpret_cast<const int *>(1)) {
+    PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return PCGB_OK;
+  }
+  if (ntiles == 0) return PCGB_OK;
+  kern<<<grid, (kConsWarps + P.bsr_prod) * 32, P.smem_bsr, st>>>(static_cast<const RP *>(P.rowptr), P.bidx, P.val, x, y, desc, P.win_start,
+                                                                  P.win_off, ntiles, P.nnz, P.cap_nnz, P.cap_nodes, P.cap_x, P.cap_blocks,
+                                                                  P.bsr_stages, P.bsr_stage_bytes, dotp, skip);
+  PCGB_CHECK_LAUNCH();
+  return PCGB_OK;
+}
+
 inline int launch_persist_any(const CsrPlan &P, const double *x, double *y, bool with_dot, cudaStream_t st, const int *skip,
                               const TileDesc *desc, int ntiles, int grid, double *dotp) {
   if (P.ntiles == 0) return PCGB_OK;
+  if (P.bsr) {
+    if (P.rp64) return with_dot ? launch_bsr_inst<true, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                                : launch_bsr_inst<false, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    return with_dot ? launch_bsr_inst<true, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
+                    : launch_bsr_inst<false, int32_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  }
   if (P.t3) {
     if (P.rp64) return with_dot ? launch_persist_lanes<true, true, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp)
                                 : launch_persist_lanes<false, true, int64_t>(P, x, y, st, skip, desc, ntiles, grid, dotp);
@@ -1231,7 +1548,7 @@ inline void free_plan(CsrPlan &P) {
   cudaFree(P.tile_row); cudaFree(P.tile_k); cudaFree(P.carry); cudaFree(P.dot_partials);
   cudaFree(P.fix_row); cudaFree(P.fix_first); cudaFree(P.fix_cnt);
   cudaFree(P.tile_xlen); cudaFree(P.tile_win); cudaFree(P.win_start); cudaFree(P.win_off); cudaFree(P.lidx);
-  cudaFree(P.tile_desc); cudaFree(P.lidx3); cudaFree(P.desc_split); cudaFree(P.dot_partials_split); cudaFree(P.diag_cache);
+  cudaFree(P.tile_desc); cudaFree(P.lidx3); cudaFree(P.bidx); cudaFree(P.desc_split); cudaFree(P.dot_partials_split); cudaFree(P.diag_cache);
 }
 
 }  // namespace pcgb

@@ -46,7 +46,8 @@ def test_spmv_variants(cuda, monkeypatch, lanes, variant):
     monkeypatch.setenv("PCGB_SPMV_TMA", "0" if variant == "ldg" else "1")
     monkeypatch.setenv("PCGB_SPMV_STAGE", "1" if variant in ("staged", "persist") else "0")
     monkeypatch.setenv("PCGB_SPMV_PERSIST", "1" if variant == "persist" else "0")
-    monkeypatch.setenv("PCGB_SPMV_T3", "0")     # one 16-bit index per non-zero (the column-triple mode has its own test)
+    monkeypatch.setenv("PCGB_SPMV_T3", "0")     # one 16-bit index per non-zero: the row-group kernels
+    monkeypatch.setenv("PCGB_SPMV_BSR", "0")    # (the node-block kernel, default for 3-dofs-per-node matrices, has its own tests)
     A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
     M = _check_spmv(A, cuda, seed=lanes)
     info = M.plan_info()
@@ -181,12 +182,13 @@ def test_spmv_triple_index(cuda, monkeypatch, lanes3, tile):
     """Column-triple index: 3 dofs per node make every row a sequence of aligned triples of consecutive columns; the
     persistent kernel then streams ONE 16-bit staged position per triple (8 + 2/3 B per non-zero instead of 10)."""
     monkeypatch.setenv("PCGB_SPMV_T3", "1")          # opt-in mode (slower than the per-non-zero index on B200 so far)
+    monkeypatch.setenv("PCGB_SPMV_BSR", "0")
     monkeypatch.setenv("PCGB_SPMV_LANES3", str(lanes3))
     monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     A = R.hex_box_csr((9, 7, 5), (0, 0, 0), (9, 7, 5))
     M = _check_spmv(A, cuda, seed=lanes3)
     info = M.plan_info()
-    assert info["triple_index"] == 1 and info["staged"] == 2 and info["lanes"] == lanes3
+    assert info["index_mode"] == 1 and info["staged"] == 2 and info["lanes"] == lanes3
     assert M.stream_bytes() < 8.8 * A.nnz + 40 * A.shape[0] + 64 * info["ntiles"]
     # an interior (unclamped) box and a box with a ragged last tile
     _check_spmv(R.hex_box_csr((8, 6, 4), (4, 0, 2), (4, 3, 2)), cuda, seed=1)
@@ -204,8 +206,9 @@ def test_spmv_triple_index(cuda, monkeypatch, lanes3, tile):
 def test_spmv_triple_index_not_applicable(cuda, monkeypatch):
     """Rows that are not made of column triples keep the per-non-zero index (Poisson: 27 single columns per row)."""
     monkeypatch.setenv("PCGB_SPMV_T3", "1")
+    monkeypatch.setenv("PCGB_SPMV_BSR", "0")
     M = _check_spmv(R.poisson27(12), cuda)
-    assert M.plan_info()["triple_index"] == 0
+    assert M.plan_info()["index_mode"] == 0
     # triples by count but not consecutive columns
     rng = np.random.default_rng(5)
     n = 300
@@ -214,17 +217,18 @@ def test_spmv_triple_index_not_applicable(cuda, monkeypatch):
     A = sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(n, n))
     A.sort_indices()
     M = _check_spmv(A, cuda, seed=2)
-    assert M.plan_info()["triple_index"] == 0
+    assert M.plan_info()["index_mode"] == 0
 
 
-@pytest.mark.parametrize("t3", ["0", "1"])
+@pytest.mark.parametrize("t3", ["0", "1", "bsr"])
 def test_spmv_interface_first_split(cuda, monkeypatch, t3):
     """Interface-first split (multi-GPU overlap): tiles owning a registered row run in a first launch, the rest in a
     second one; y is bit-identical to the single launch (same tiles, same arithmetic), x.y agrees to rounding."""
     import torch
     from pcg_mpi_solver_b200.csr import CsrMatrix
-    monkeypatch.setenv("PCGB_SPMV_T3", t3)
-    monkeypatch.setenv("PCGB_SPMV_TILE", "512")
+    monkeypatch.setenv("PCGB_SPMV_T3", "1" if t3 == "1" else "0")
+    monkeypatch.setenv("PCGB_SPMV_BSR", "1" if t3 == "bsr" else "0")
+    monkeypatch.setenv("PCGB_SPMV_TILE", "512" if t3 != "bsr" else "768")
     A = R.hex_box_csr((12, 10, 8), (0, 0, 0), (12, 10, 8))
     n = A.shape[0]
     M = CsrMatrix.from_scipy(A, device=cuda)
@@ -269,3 +273,51 @@ def test_release_col(cuda):
     P = CsrMatrix.from_scipy(R.poisson27(6), device=cuda)
     if P.plan_info()["staged"] != 2:
         assert not P.release_col() and P.col is not None
+
+
+@pytest.mark.parametrize("tile", [0, 600, 1200, 4300])
+def test_spmv_node_block_kernel(cuda, monkeypatch, tile):
+    """Node-block ("BSR-3") kernel, the default for 3-dofs-per-node matrices: one thread per 3x3 block, one 16-bit staged position
+    per block (8 + 2/9 B per non-zero), rows summed from shared-memory partials in block order.  Several tile sizes (one and
+    several passes of 256 blocks, 2- and 4-stage rings), clamped / interior boxes, fused dot, bit-reproducibility."""
+    import torch
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    if tile:
+        monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
+    for box in [((9, 7, 5), (0, 0, 0), (9, 7, 5)), ((8, 6, 4), (4, 0, 2), (4, 3, 2)), ((14, 12, 10), (0, 0, 0), (14, 12, 10))]:
+        A = R.hex_box_csr(*box)
+        M = _check_spmv(A, cuda, seed=tile)
+        info = M.plan_info()
+        assert info["index_mode"] == 2 and info["staged"] == 2 and info["split_rows"] == 0, info
+        assert M.stream_bytes() < 8.3 * A.nnz + 40 * A.shape[0] + 64 * info["ntiles"]
+        x = torch.from_numpy(np.random.default_rng(1).standard_normal(A.shape[0])).to(cuda)
+        y = M.spmv(x).clone()
+        assert torch.equal(M.spmv(x), y)                                   # fixed summation order
+        M.set_boundary_rows(torch.arange(0, A.shape[0], 11, dtype=torch.int32, device=cuda))
+        y2, d = M.spmv_split(x, with_dot=True)
+        assert torch.equal(y2, y)
+        ref = float(torch.dot(x, y))
+        assert abs(float(d) - ref) <= 1e-12 * float(torch.dot(x.abs(), y.abs()))
+
+
+def test_spmv_node_block_irregular_nodes(cuda):
+    """Nodes with different numbers of blocks per row (a random node graph expanded to 3x3 blocks) - the octree / concrete shape."""
+    rng = np.random.default_rng(12)
+    nn = 700
+    rows, cols = [], []
+    for n in range(nn):
+        k = int(rng.integers(1, 40))
+        nb = np.unique(np.concatenate([[n], rng.choice(nn, k, replace=False)]))
+        rows.append(np.full(nb.size, n)); cols.append(nb)
+    G = sp.csr_matrix((np.ones(sum(c.size for c in cols)), (np.concatenate(rows), np.concatenate(cols))), shape=(nn, nn))
+    A = sp.kron(G, np.ones((3, 3))).tocsr()
+    A.data = rng.standard_normal(A.nnz)
+    A.sort_indices()
+    M = _check_spmv(A, cuda, seed=4)
+    assert M.plan_info()["index_mode"] == 2
+    # one row of one node differs from its siblings -> not a node-block matrix -> row-group kernel, same answer
+    B = A.tolil()
+    B[4, 5 if B[4, 5] == 0 else 6] = 1.0 if B[4, 5] == 0 else 0.0
+    B = B.tocsr(); B.eliminate_zeros(); B.sort_indices()
+    M = _check_spmv(B, cuda, seed=5)
+    assert M.plan_info()["index_mode"] == 0

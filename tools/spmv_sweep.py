@@ -10,15 +10,16 @@ blk = HexBlock((blk_n,) * 3, (0, 0, 0), (blk_n,) * 3, h=1.0 / blk_n)
 base = generate_matrix(blk, device=dev)
 x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
-T3 = {"PCGB_SPMV_T3": 1}
+BSR = {"PCGB_SPMV_BSR": 1}
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or [
-    {"PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
-    *[{**T3, "PCGB_SPMV_LANES3": l, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for l in (8, 16, 32)],
-    *[{**T3, "PCGB_SPMV_LANES3": 16, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for t in (1792, 2048, 2560, 2816, 3072)],
-    *[{**T3, "PCGB_SPMV_LANES3": 8, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for t in (2048, 2816)],
-    {**T3, "PCGB_SPMV_LANES3": 16, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 8, "PCGB_SPMV_CTAS": 1},
-    {**T3, "PCGB_SPMV_LANES3": 16, "PCGB_SPMV_TILE": 1536, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3},
-    {**T3, "PCGB_SPMV_LANES3": 16, "PCGB_SPMV_TILE": 4096, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 1}]
+    {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
+    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for t in (1812, 2058, 2304)],
+    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2} for t in (4362, 3072)],
+    {**BSR, "PCGB_SPMV_TILE": 4362, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 1},
+    {**BSR, "PCGB_SPMV_TILE": 2058, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 3},
+    {**BSR, "PCGB_SPMV_TILE": 2058, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 4},
+    {**BSR, "PCGB_SPMV_TILE": 1320, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3},
+    {**BSR, "PCGB_SPMV_TILE": 1074, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 4}]
 for cfg in configs:
     for k, v in cfg.items():
         os.environ[k] = str(v)
@@ -34,6 +35,6 @@ for cfg in configs:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(json.dumps({**cfg, "ms": round(ms, 4), "GBps": round(M.spmv_bytes() / ms / 1e6, 1), "smem": M.plan_info()["smem_bytes"], "staged": M.plan_info()["staged"], "xcap": M.plan_info()["x_cap"], "maxw": M.plan_info()["max_windows_per_tile"], "t3": M.plan_info()["triple_index"], "lanes": M.plan_info()["lanes"],
+    print(json.dumps({**cfg, "ms": round(ms, 4), "GBps": round(M.spmv_bytes() / ms / 1e6, 1), "smem": M.plan_info()["smem_bytes"], "staged": M.plan_info()["staged"], "xcap": M.plan_info()["x_cap"], "maxw": M.plan_info()["max_windows_per_tile"], "mode": M.plan_info()["index_mode"], "lanes": M.plan_info()["lanes"],
                       "streamGBps": round(M.stream_bytes() / ms / 1e6, 1), "ctas": M.plan_info()["resident_ctas"]}), flush=True)
     del M
