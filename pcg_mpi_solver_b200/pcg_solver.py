@@ -185,37 +185,51 @@ def run(run_id, speed_test: int = 0, workdir: str = ".", backend=None, quiet: bo
     own_node = own_dof[0::3]
     export_count = 0
     times_t = []
-    if export_flag:                                                    # initExportData :195-209
-        write_mpi_file(vec_path + "Dof", sub.dof_vector[own_dof], ranks)
-        write_mpi_file(vec_path + "NodeId", sub.node_ids[own_node], ranks)
-        write_mpi_file(vec_path + "U_0", un[own_dof], ranks)
-        times_t.append(0.0)
+    # ExportFrms is a nested 1-based list in the reference: np.array(ExportFrms, int)[0] - 1  (initExportData, :156-159)
+    frms = np.array(th["ExportFrms"], dtype=int)
+    frms = (frms[0] - 1) if len(frms) > 0 else frms
+    frms = set(int(v) for v in np.atleast_1d(frms))
+    rate = th["ExportFrmRate"]
+
+    def export_now(step):                                              # exportContourData :854-859
+        return (rate > 0 and step % rate == 0) or (step in frms)
+
+    def export_frame(step):
+        nonlocal export_count
+        write_mpi_file(vec_path + "U_" + str(export_count), un[own_dof], ranks)   # :867-869
+        times_t.append(step * dt)                                      # TimeList[TimeStepCount] = TimeStepCount*dt (:167)
         if ranks.rank == 0:
             np.save(vec_path + "Time_T", times_t)
-        export_count = 1
+        export_count += 1
+
+    if export_flag:                                                    # initExportData :195-209 (calls exportContourData at step 0)
+        write_mpi_file(vec_path + "Dof", sub.dof_vector[own_dof], ranks)
+        write_mpi_file(vec_path + "NodeId", sub.node_ids[own_node], ranks)
+        if export_now(0):
+            export_frame(0)
     flags, relres, iters = np.zeros(nsteps), np.zeros(nsteps), np.zeros(nsteps)
     from .partition import _ebe_matvec
     for step in range(1, nsteps):                                      # :1002-1008
         delta = deltas[step]
         udi = sub.Ud * delta                                           # updateBC :234-238
         fdi = np.zeros(sub.ndof)
-        if any(ranks.gather(bool(np.any(udi != 0)))):                  # K (Ud delta), summed over the parts sharing a dof
-            loc = _ebe_matvec(sub.groups, udi, sub.ndof)
-            for glob_idx, vals in ranks.gather((sub.dof_vector, loc)):
-                sel = np.isin(glob_idx, sub.dof_vector)
-                np.add.at(fdi, np.searchsorted(sub.dof_vector, glob_idx[sel]), vals[sel])
+        if any(ranks.gather(bool(np.any(udi != 0)))):                  # K (Ud delta) + the interface sum of calcMPFint (:303-334):
+            fdi = _ebe_matvec(sub.groups, udi, sub.ndof)               # only the overlap dofs travel, neighbour by neighbour
+            sends = ranks.gather({q: fdi[idx] for q, idx in zip(sub.nbr, sub.ovrlp_full)})
+            recv = [sends[q][ranks.rank] for q in sub.nbr]
+            for idx, vals in zip(sub.ovrlp_full, recv):                # += in neighbour order (:332-334)
+                fdi[idx] += vals
         fext = sub.F * delta - fdi
         x, flag, rr, it = solve_step(fext[eff], un[eff], sp["Tol"], sp["MaxIter"])
-        flags[step], relres[step], iters[step] = flag, rr, it          # :593-596
-        xunq = np.zeros(sub.ndof)
-        xunq[eff] = x
-        un = xunq + udi                                                # :598
-        if export_flag and ((th["ExportFrmRate"] > 0 and step % th["ExportFrmRate"] == 0) or step in list(th["ExportFrms"])):
-            write_mpi_file(vec_path + "U_" + str(export_count), un[own_dof], ranks)   # exportContourData :867-869
-            times_t.append(step * dt)
-            if ranks.rank == 0:
-                np.save(vec_path + "Time_T", times_t)
-            export_count += 1
+        if it > 0 or flag != 0:
+            flags[step], relres[step], iters[step] = flag, rr, it      # :593-596
+            xunq = np.zeros(sub.ndof)
+            xunq[eff] = x
+            un = xunq + udi                                            # :598
+        # else: PCG returned early (zero right-hand side or initial guess good enough, :387-395, :421-426): the reference's
+        # early `return` leaves RefMeshPart['Un'] and the TimeList_* entries untouched
+        if export_flag and export_now(step):
+            export_frame(step)
     t_end = time()
     rec = ranks.gather({"dT_FileRead": t_read, "dT_Calc": t_end - t_start, "dT_CommWait": 0.0, "t0_Start": t_start, "t0_End": t_end})
     if ranks.rank == 0:                                                # exportTimeData :943-961 / configTimeRecData

@@ -109,6 +109,39 @@ def test_cli_reads_the_reference_builders_fixture_cpu(tmp_path):
     assert np.linalg.norm(b - A @ x) <= 1e-10 * np.linalg.norm(b) * (1 + 1e-6)
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/solver/pcg_solver.py"), reason="needs the reference checkout")
+@pytest.mark.parametrize("rate,frms", [(0, [[2, 3]]), (2, [[2]]), (0, [])])
+def test_cli_export_frames_match_the_reference(tmp_path, rate, frms):
+    """ExportFrms is a NESTED, 1-BASED list (np.array(ExportFrms, int)[0] - 1, pcg_solver.py:156-159) and the step-0 frame is
+    written only when the ExportNow predicate holds for step 0 (:854-859): same set of U_k files, same contents, same Time_T
+    as the unmodified reference run on the same fixture."""
+    from pcg_mpi_solver_b200.pcg_solver import run
+    work, mdf, info = _setup_workdir(tmp_path, (4, 3, 3), 1e-11, 2000)
+    rr.metis_stage(work, 1)
+    rr.partition_stage(work, 1)
+    settings = {"TimeHistoryParam": {"ExportFlag": True, "ExportFrmRate": rate, "ExportFrms": frms, "PlotFlag": False,
+                                     "TimeStepDelta": [0, 0.25, 0.5, 1.0], "ExportVars": "U"}, "SolverParam": {"Tol": 1e-11, "MaxIter": 2000}}
+    with open(os.path.join(work, "__pycache__", "GlobSettings.zpkl"), "wb") as f:
+        f.write(zlib.compress(pickle.dumps(settings, pickle.HIGHEST_PROTOCOL)))
+    rr.solve_stage(work, 1, run_id=1)                                    # the unmodified reference
+    run(2, 0, workdir=work, backend=_oracle_backend, quiet=True)         # the file-compatible stage
+    ref_dir = os.path.join(work, "data", "Results_Run1", "ResVecData")
+    our_dir = os.path.join(work, "data", "Results_Run2", "ResVecData")
+    ref_files = sorted(f for f in os.listdir(ref_dir) if f.endswith(".mpidat"))
+    assert sorted(f for f in os.listdir(our_dir) if f.endswith(".mpidat")) == ref_files
+    for f in ref_files:
+        a, b = np.fromfile(os.path.join(ref_dir, f), dtype=np.uint8), np.fromfile(os.path.join(our_dir, f), dtype=np.uint8)
+        if f.startswith("U_"):
+            ua, ub = a.view(np.float64), b.view(np.float64)
+            assert ua.shape == ub.shape and np.linalg.norm(ua - ub) <= 1e-9 * max(np.linalg.norm(ua), 1e-300)
+        else:
+            assert np.array_equal(a, b)
+    if os.path.exists(os.path.join(ref_dir, "Time_T.npy")):
+        assert list(np.load(os.path.join(ref_dir, "Time_T.npy"))) == list(np.load(os.path.join(our_dir, "Time_T.npy")))
+    else:
+        assert not os.path.exists(os.path.join(our_dir, "Time_T.npy"))
+
+
 @pytest.mark.gpu
 def test_cli_on_gpu_matches_reference_golden(cuda, tmp_path):
     """Same pipeline with the CUDA backend (device assembly + pcgb_solve) against the reference's golden run."""
