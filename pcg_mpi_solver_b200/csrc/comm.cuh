@@ -150,7 +150,7 @@ namespace pcgb {
 // that the solver can put the interior SpMV tiles between them (halo_pack / halo_unpack); NCCL transport: serial.
 inline int halo_pack(pcgb_halo_t h, const double *y, cudaStream_t st, int *launches = nullptr) {
   if (!h || h->m == 0) return PCGB_OK;
-  k_halo_pack_peer<<<(unsigned)((h->m + 255) / 256), 256, 0, st>>>(h->peer_view(), h->d_idx, y);
+  k_halo_pack_peer<<<(unsigned)((h->m + 256 * kPackPerThread - 1) / (256 * kPackPerThread)), 256, 0, st>>>(h->peer_view(), h->d_idx, y);
   PCGB_CHECK_LAUNCH();
   if (launches) *launches += 1;
   return PCGB_OK;

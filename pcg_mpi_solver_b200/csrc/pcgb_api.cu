@@ -57,12 +57,15 @@ struct pcgb_solver_s {
   PcgCtrl *h_ctrl = nullptr;    // pinned
   double *h_red = nullptr;      // pinned [8]
   cudaStream_t own = nullptr;   // the solve runs here: the caller's stream may be the legacy stream, which cannot be captured
+  cudaStream_t side = nullptr;  // fork of the iteration: the halo unpack-add runs beside the p.q all-reduce
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_l0 = nullptr, ev_l1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   std::vector<cudaEvent_t> ev_k;  // SpMV brackets (time_kernels)
   cudaGraphExec_t gexec = nullptr;
   GraphKey gkey{nullptr, nullptr, nullptr, nullptr, 0};
   int launches = 0;             // launches issued outside graphs (running counter per solve)
   int launches_per_iter = 0;
+  bool fork_halo = true;        // PCGB_FORK=0 keeps the unpack on the main stream
 };
 
 static int require_device() {
@@ -756,6 +759,7 @@ static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pc
   PCGB_TRY(require_device());
   pcgb_solver_t s = new pcgb_solver_s();
   s->A = A; s->E = E; s->halo = halo; s->comm = comm; s->n = A ? A->P.nrows : E->P.n;
+  s->fork_halo = env_int("PCGB_FORK", 1) != 0;
   const size_t nb = (size_t)(s->n > 0 ? s->n : 1) * sizeof(double);
   s->stage_cap = ((A ? A->P.ntiles : 0) + 4095) / 4096 + 1;
   cudaError_t ce = cudaSuccess;
@@ -769,6 +773,9 @@ static int solver_create_common(pcgb_csr_t A, pcgb_ebe_t E, pcgb_halo_t halo, pc
       (ce = cudaMalloc(&s->d_ctrl, sizeof(PcgCtrl))) == cudaSuccess && (ce = cudaMallocHost(&s->h_ctrl, sizeof(PcgCtrl))) == cudaSuccess &&
       (ce = cudaMallocHost(&s->h_red, 8 * sizeof(double))) == cudaSuccess &&
       (ce = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking)) == cudaSuccess &&
+      (ce = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking)) == cudaSuccess &&
+      (ce = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) == cudaSuccess &&
+      (ce = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming)) == cudaSuccess &&
       (ce = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming)) == cudaSuccess &&
       (ce = cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming)) == cudaSuccess &&
       (ce = cudaEventCreate(&s->ev_l0)) == cudaSuccess && (ce = cudaEventCreate(&s->ev_l1)) == cudaSuccess &&
@@ -800,6 +807,9 @@ int pcgb_solver_destroy(pcgb_solver_t s) {
   if (!s) return PCGB_OK;
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->own) cudaStreamDestroy(s->own);
+  if (s->side) cudaStreamDestroy(s->side);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->ev_in) cudaEventDestroy(s->ev_in);
   if (s->ev_out) cudaEventDestroy(s->ev_out);
   if (s->ev_l0) cudaEventDestroy(s->ev_l0);
@@ -938,11 +948,21 @@ int enqueue_iteration(pcgb_solver_t s, const double *minv, const double *w, doub
     // own kernels over peer memory: the all-reduce is fused into the reduction kernel, the scalar logic follows in the same CTA
     if (s->halo && !halo_done) PCGB_TRY(halo_pack(s->halo, s->q, st, nl));
     const PeerWin win = s->comm->window();
+    // fork: the unpack-add of the interface values (waits for the neighbours' stores) runs beside the p.q all-reduce (waits
+    // for the other ranks' sums); both only need the pack above, which never waits - so no order of execution can deadlock
+    const bool fork = s->halo && s->halo->m > 0 && s->side != nullptr && s->fork_halo;
+    if (fork) {
+      PCGB_CUDA(cudaEventRecord(s->ev_fork, st));
+      PCGB_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+      PCGB_TRY(halo_unpack(s->halo, s->q, s->side, nl));
+      PCGB_CUDA(cudaEventRecord(s->ev_join, s->side));
+    }
     k_reduce_ar<1, 1><<<1, 256, 0, st>>>(win, s->d_ctrl, pq_src, pq_cnt, 0, s->red, nullptr);
     PCGB_CHECK_LAUNCH();
     *nl += 1;
     PCGB_MARK(5);
-    if (s->halo) PCGB_TRY(halo_unpack(s->halo, s->q, st, nl));
+    if (fork) PCGB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+    else if (s->halo) PCGB_TRY(halo_unpack(s->halo, s->q, st, nl));
     PCGB_MARK(6);
     k_update<<<vg, kVecBlock, 0, st>>>(s->d_ctrl, n, s->r, s->q, s->p, minv, w, xb0, s->xalt, s->partials);
     PCGB_CHECK_LAUNCH();

@@ -165,20 +165,29 @@ struct PeerHalo {
   int *status = nullptr;
 };
 
-// send[i] = y[idx[i]] stored directly into the neighbour's receive buffer; the last CTA releases the flags
+// send[i] = y[idx[i]] stored directly into the neighbour's receive buffer; the last CTA releases the flags.
+// kPackPerThread entries per thread; ONE system fence per CTA (bar.sync makes the CTA's stores visible to thread 0, whose
+// fence.sys is cumulative - the grid-sync idiom) instead of one per thread: the fence waits for the NVLink write acks.
+constexpr int kPackPerThread = 4;
 __global__ void __launch_bounds__(256)
 k_halo_pack_peer(PeerHalo h, const int *__restrict__ idx, const double *__restrict__ y) {
   __shared__ bool s_last;
   const unsigned long long ep = *h.epoch + 1;   // only the last CTA advances it, after every CTA has read it
   const int par = (int)(ep & 1ull);
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < h.m) {
-    const int j = h.ent_nbr[i];
-    h.remote[j][(size_t)par * (size_t)h.remote_m[j] + (size_t)(i - h.nbr_ptr[j])] = y[idx[i]];
+  const int64_t base = blockIdx.x * (int64_t)(256 * kPackPerThread) + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kPackPerThread; ++u) {
+    const int64_t i = base + u * 256;
+    if (i < h.m) {
+      const int j = h.ent_nbr[i];
+      h.remote[j][(size_t)par * (size_t)h.remote_m[j] + (size_t)(i - h.nbr_ptr[j])] = y[idx[i]];
+    }
   }
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(h.done, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(h.done, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();

@@ -838,7 +838,7 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
         nd0 = __ldg(dp); nd1 = __ldg(dp + 1);
       }
       const int64_t k0 = ((int64_t)(uint32_t)d0.x) | ((int64_t)d0.y << 32);
-      const int cnt = d0.z, r0 = d0.w, R = d1.x & 0x7fffffff, wb = d1.y, nw = d1.z, xlen = d1.w;
+      const int cnt = d0.z, r0 = d0.w, R = d1.x & 0x3fffffff, uni = (d1.x >> 30) & 1, wb = d1.y, nw = d1.z, xlen = d1.w;
       unsigned char *base = smem_raw + (size_t)s * stage_bytes;
       double *sval = reinterpret_cast<double *>(base);
       double *sx = reinterpret_cast<double *>(base + off_sx);
@@ -861,7 +861,7 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
         if (nb > 0) bulk_g2s(sval, val + ka, (uint32_t)nb * 8u, &full_bar[s], pol);
         if (ib > 0) bulk_g2s(sb, bidx + ba, ib, &full_bar[s], pol);
         meta[0] = r0; meta[1] = R; meta[2] = tile; meta[3] = cnt;
-        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32); meta[6] = (int)(b0 - ba);
+        meta[4] = (int)(k0 & 0xffffffff); meta[5] = (int)(k0 >> 32); meta[6] = (int)(b0 - ba); meta[7] = uni;
       }
       {
         const int64_t lim = nnz & ~(int64_t)kAlignMask;
@@ -918,40 +918,60 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     const int NN = R / 3, NB = cnt / 9;
     const uint16_t *sbt = sb + meta[6];
     const double *svt = sval + k0l;
+    // uniform tile (all nodes have the same number of blocks - the interior of a structured mesh): node = b / Lb, no look-ups
+    const bool uni = meta[7] != 0 && NN > 0;
+    const int Lbu = uni ? NB / NN : 0;
     // block offset of every node (kept for phase 2, which runs after the stage has been handed back)
-    for (int i = tid; i <= NN; i += NT) nbo[i] = (int)((int64_t)snp[i] - k0) / 9;
+    for (int i = tid; i <= NN; i += NT) nbo[i] = uni ? i * Lbu : (int)((int64_t)snp[i] - k0) / 9;
     // ---- phase 1: one 3x3 block per thread and pass
     for (int b = tid; b < NB; b += NT) {
-      int lo = 0, hi = NN - 1;                     // node of block b: last i with (snp[i] - k0) <= 9 b
-      const int kb = 9 * b;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)((int64_t)snp[mid] - k0) <= kb) lo = mid; else hi = mid - 1;
+      int noff, L, t3;
+      if (uni) {
+        const int i = b / Lbu;
+        noff = i * 9 * Lbu; L = 3 * Lbu; t3 = 3 * (b - i * Lbu);
+      } else {
+        int lo = 0, hi = NN - 1;                     // node of block b: last i with (snp[i] - k0) <= 9 b
+        const int kb = 9 * b;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((int)((int64_t)snp[mid] - k0) <= kb) lo = mid; else hi = mid - 1;
+        }
+        noff = (int)((int64_t)snp[lo] - k0);
+        L = ((int)((int64_t)snp[lo + 1] - k0) - noff) / 3;   // non-zeros per row of this node
+        t3 = (kb - noff) / 3;                                  // 3 t, t = b - noff / 9
       }
-      const int noff = (int)((int64_t)snp[lo] - k0);
-      const int L = ((int)((int64_t)snp[lo + 1] - k0) - noff) / 3;   // non-zeros per row of this node
       const int ii = sbt[b];
-      const double *pv = svt + noff + (kb - noff) / 3;                 // 3 t, t = b - noff / 9
+      const double *pv = svt + noff + t3;
       const double x0 = sx[ii], x1 = sx[ii + 1], x2 = sx[ii + 2];
-      const double p0 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
-      pv += L;
-      const double p1 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
-      pv += L;
-      const double p2 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
+      const double a0 = pv[0], a1 = pv[1], a2 = pv[2];
+      const double b0 = pv[L], b1 = pv[L + 1], b2 = pv[L + 2];
+      const double c0 = pv[2 * L], c1 = pv[2 * L + 1], c2 = pv[2 * L + 2];
       double *pp = part + 3 * b;
-      pp[0] = p0; pp[1] = p1; pp[2] = p2;
+      pp[0] = fma(a2, x2, fma(a1, x1, a0 * x0));
+      pp[1] = fma(b2, x2, fma(b1, x1, b0 * x0));
+      pp[2] = fma(c2, x2, fma(c1, x1, c0 * x0));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);     // the stage is free: everything phase 2 needs is in the scratch
     named_bar_sync(1, NT);
-    // ---- phase 2: one row per thread, partials added in block order
-    for (int r = tid; r < R; r += NT) {
-      const int i = r / 3, k = r - 3 * i;
-      const int b0 = nbo[i], b1 = nbo[i + 1];
+    // ---- phase 2: 8 lanes per row, each adds a contiguous run of the row's partials (block order), then a fixed shuffle tree
+    for (int rb = 0; rb < R; rb += NT / 8) {         // warp-uniform trip count (full-mask shuffles)
+      const int r = rb + (tid >> 3), j = tid & 7;
+      const bool live = r < R;
       double acc = 0.0;
-      for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
-      y[r0 + r] = acc;
-      if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
+      if (live) {
+        const int i = r / 3, k = r - 3 * i;
+        const int b0 = nbo[i], nblk = nbo[i + 1] - b0;
+        const int chunk = (nblk + 7) >> 3;
+        int lo = b0 + j * chunk, hi = lo + chunk;
+        if (hi > b0 + nblk) hi = b0 + nblk;
+        for (int b = lo; b < hi; ++b) acc += part[3 * b + k];
+      }
+      acc = group_sum<8>(acc);
+      if (live && j == 0) {
+        y[r0 + r] = acc;
+        if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
+      }
     }
   }
   if (DOT) {
@@ -967,6 +987,19 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
 }
 
 // ---- node-block plan helpers
+// bit 30 of TileDesc.R: every row of the tile has the same length (uniform nodes -> no per-block node search in the kernel)
+template <typename RP>
+__global__ void k_mark_uniform(const RP *__restrict__ rowptr, TileDesc *__restrict__ desc, int ntiles) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ntiles) return;
+  const int r0 = desc[b].r0, R = desc[b].R & 0x3fffffff;
+  if (R <= 0) return;
+  const int64_t L0 = (int64_t)rowptr[r0 + 1] - (int64_t)rowptr[r0];
+  bool uni = true;
+  for (int i = 1; i < R; ++i) uni = uni && ((int64_t)rowptr[r0 + i + 1] - (int64_t)rowptr[r0 + i] == L0);
+  if (uni) desc[b].R |= 0x40000000;
+}
+
 // eligibility: rows 3n, 3n+1, 3n+2 have one length (a multiple of 3) and one column pattern made of aligned consecutive triples
 template <typename RP>
 __global__ void k_check_bsr3(const RP *__restrict__ rowptr, const int *__restrict__ col, int64_t nnodes, int *__restrict__ fail) {
@@ -1022,7 +1055,7 @@ __global__ void k_flag_tiles(const TileDesc *__restrict__ desc, int ntiles, cons
                              unsigned char *__restrict__ tileflag) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= ntiles) return;
-  const int r0 = desc[b].r0, R = desc[b].R & 0x7fffffff;
+  const int r0 = desc[b].r0, R = desc[b].R & 0x3fffffff;   // bit 31: head continuation, bit 30: uniform nodes
   unsigned char f = 0;
   for (int i = 0; i < R; ++i) f |= rowflag[r0 + i];
   tileflag[b] = f;
@@ -1117,8 +1150,8 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   if (bsr_ok) {
     // one 3x3 block per consumer thread and pass (256 threads): a tile of at most 256 (or 512) blocks whatever the node snap does
     const int node_items = 3 * (P.max_row + 1);
-    int t = 2304 - node_items;
-    if (t < 1536) t = 4608 - node_items;
+    int t = 2304 - node_items;                             // <= 256 blocks whatever the snap does: one pass of 256 threads
+    if (t < 1536) t = 2304;                                // long node rows (octree meshes): allow a second, partly filled pass
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1265,7 +1298,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
           if (fit < 1) fit = 1;
           P.ctas_per_sm = std::min(ctas > 0 ? ctas : 1, fit);
           P.grid_persist = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
-          if (P.persist && bsr_ok) {
+          if (bsr_ok && P.dot_partials != nullptr) {
             // node-block index stream from the per-non-zero positions of the same (node-aligned) tiles
             PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
             const int64_t nblk = P.nnz / 9;
@@ -1299,6 +1332,10 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             if (bfit < 1) bfit = 1;
             P.bsr = h_fb == 0 && P.smem_bsr <= 200 * 1024;
             if (P.bsr) {
+              P.persist = true;
+              k_mark_uniform<RP><<<(P.ntiles + 255) / 256, 256, 0, st>>>(rp, P.tile_desc, P.ntiles);
+              PCGB_CHECK_LAUNCH();
+              PCGB_CUDA(cudaStreamSynchronize(st));
               P.ctas_per_sm = std::min(bct > 0 ? bct : 1, bfit);
               P.grid_bsr = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
               P.grid_persist = P.grid_bsr; P.smem_persist = P.smem_bsr; P.stages = P.bsr_stages; P.stage_bytes = P.bsr_stage_bytes;
