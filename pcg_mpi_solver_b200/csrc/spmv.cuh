@@ -77,7 +77,7 @@ struct CsrPlan {
   // non-zero from HBM, a third of the x gathers and a ninth of the index loads of the row-group consumer
   bool bsr = false;
   uint16_t *bidx = nullptr;        // [nnz/9 + 16]  staged x position of block t of node n at rowptr[3n]/9 + t
-  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0;
+  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0, bsr_mode = 1;
   // interface-first split (multi-GPU overlap): tiles that own an interface row are listed first in desc_split
   struct TileDesc *desc_split = nullptr;  // [ntiles] permutation of tile_desc
   int nb_tiles = 0;                       // leading boundary tiles of desc_split
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__((kConsWarps + 4) * 32)
 k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, const double *__restrict__ val,
             const double *__restrict__ x, double *__restrict__ y, const TileDesc *__restrict__ desc,
             const int *__restrict__ win_start, const int *__restrict__ win_off, int ntiles, int64_t nnz, int cap_nnz,
-            int cap_nodes, int cap_x, int cap_blocks, int stages, int stage_bytes, double *__restrict__ dot_partials,
+            int cap_nodes, int cap_x, int cap_blocks, int stages, int stage_bytes, int mode, double *__restrict__ dot_partials,
             const int *__restrict__ skip) {
   if (skip != nullptr && *skip != 0) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -919,15 +919,16 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     const uint16_t *sbt = sb + meta[6];
     const double *svt = sval + k0l;
     // uniform tile (all nodes have the same number of blocks - the interior of a structured mesh): node = b / Lb, no look-ups
-    const bool uni = meta[7] != 0 && NN > 0;
+    const bool uni = (mode & 1) != 0 && meta[7] != 0 && NN > 0;
     const int Lbu = uni ? NB / NN : 0;
+    const unsigned magic = uni ? (unsigned)((0xffffffffull + (unsigned)Lbu) / (unsigned)Lbu) : 0u;   // b / Lbu = (b * magic) >> 32 for b < 2^16
     // block offset of every node (kept for phase 2, which runs after the stage has been handed back)
     for (int i = tid; i <= NN; i += NT) nbo[i] = uni ? i * Lbu : (int)((int64_t)snp[i] - k0) / 9;
     // ---- phase 1: one 3x3 block per thread and pass
     for (int b = tid; b < NB; b += NT) {
       int noff, L, t3;
       if (uni) {
-        const int i = b / Lbu;
+        const int i = (int)__umulhi((unsigned)b, magic);
         noff = i * 9 * Lbu; L = 3 * Lbu; t3 = 3 * (b - i * Lbu);
       } else {
         int lo = 0, hi = NN - 1;                     // node of block b: last i with (snp[i] - k0) <= 9 b
@@ -954,7 +955,20 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);     // the stage is free: everything phase 2 needs is in the scratch
     named_bar_sync(1, NT);
-    // ---- phase 2: 8 lanes per row, each adds a contiguous run of the row's partials (block order), then a fixed shuffle tree
+    if ((mode & 2) == 0) {
+      // ---- phase 2 (default): one row per thread, partials added in block order.  Only the first warp(s) are busy here; the
+      //      others already wait for / start on the next tile, so this overlaps with the next phase 1.
+      for (int r = tid; r < R; r += NT) {
+        const int i = r / 3, k = r - 3 * i;
+        const int b0 = nbo[i], b1 = nbo[i + 1];
+        double acc = 0.0;
+        for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
+        y[r0 + r] = acc;
+        if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
+      }
+      continue;
+    }
+    // ---- phase 2 (mode bit 1): 8 lanes per row, each adds a contiguous run of the row's partials, then a fixed shuffle tree
     for (int rb = 0; rb < R; rb += NT / 8) {         // warp-uniform trip count (full-mask shuffles)
       const int r = rb + (tid >> 3), j = tid & 7;
       const bool live = r < R;
@@ -989,7 +1003,7 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
 // ---- node-block plan helpers
 // bit 30 of TileDesc.R: every row of the tile has the same length (uniform nodes -> no per-block node search in the kernel)
 template <typename RP>
-__global__ void k_mark_uniform(const RP *__restrict__ rowptr, TileDesc *__restrict__ desc, int ntiles) {
+__global__ void k_mark_uniform(const RP *__restrict__ rowptr, TileDesc *__restrict__ desc, int ntiles, int *__restrict__ count) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= ntiles) return;
   const int r0 = desc[b].r0, R = desc[b].R & 0x3fffffff;
@@ -997,16 +1011,19 @@ __global__ void k_mark_uniform(const RP *__restrict__ rowptr, TileDesc *__restri
   const int64_t L0 = (int64_t)rowptr[r0 + 1] - (int64_t)rowptr[r0];
   bool uni = true;
   for (int i = 1; i < R; ++i) uni = uni && ((int64_t)rowptr[r0 + i + 1] - (int64_t)rowptr[r0 + i] == L0);
-  if (uni) desc[b].R |= 0x40000000;
+  if (uni) { desc[b].R |= 0x40000000; atomicAdd(count, 1); }
 }
 
 // eligibility: rows 3n, 3n+1, 3n+2 have one length (a multiple of 3) and one column pattern made of aligned consecutive triples
 template <typename RP>
-__global__ void k_check_bsr3(const RP *__restrict__ rowptr, const int *__restrict__ col, int64_t nnodes, int *__restrict__ fail) {
+__global__ void k_check_bsr3(const RP *__restrict__ rowptr, const int *__restrict__ col, int64_t nnodes, int *__restrict__ fail,
+                             unsigned long long *__restrict__ same_as_next) {
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
     const int64_t a0 = rowptr[3 * n], a1 = rowptr[3 * n + 1], a2 = rowptr[3 * n + 2], a3 = rowptr[3 * n + 3];
     const int64_t L = a1 - a0;
     if (a2 - a1 != L || a3 - a2 != L || L % 3 != 0) { *fail = 1; return; }
+    // regularity of the mesh: how many nodes have as many blocks as their successor (structured meshes: almost all)
+    if (n + 1 < nnodes && (int64_t)rowptr[3 * n + 4] - a3 == L) atomicAdd(same_as_next, 1ull);
     for (int64_t t = 0; t < L; t += 3) {
       const int c = col[a0 + t];
       if (col[a0 + t + 1] != c + 1 || col[a0 + t + 2] != c + 2) { *fail = 1; return; }
@@ -1139,19 +1156,29 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   bool bsr_ok = false;
   if (P.use_tma && P.nrows > 0 && P.nrows % 3 == 0 && P.nnz % 9 == 0 && P.nnz > 0 && env_int("PCGB_SPMV_BSR", 1) != 0 &&
       env_int("PCGB_SPMV_STAGE", 1) != 0 && env_int("PCGB_SPMV_PERSIST", 1) != 0 && env_int("PCGB_SPMV_SNAP", 1) != 0) {
+    unsigned long long *d_same = nullptr, h_same = 0;
+    PCGB_CUDA(cudaMalloc(&d_same, sizeof(unsigned long long)));
+    PCGB_CUDA(cudaMemsetAsync(d_same, 0, sizeof(unsigned long long), st));
     PCGB_CUDA(cudaMemsetAsync(d_stats + 3, 0, sizeof(int), st));
-    k_check_bsr3<RP><<<(int)std::min<int64_t>((P.nrows / 3 + 127) / 128, 148 * 16), 128, 0, st>>>(rp, P.col, P.nrows / 3, d_stats + 3);
-    PCGB_CHECK_LAUNCH();
-    PCGB_CUDA(cudaMemcpyAsync(h_stats + 3, d_stats + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PCGB_CUDA(cudaStreamSynchronize(st));
-    bsr_ok = h_stats[3] == 0;
+    k_check_bsr3<RP><<<(int)std::min<int64_t>((P.nrows / 3 + 127) / 128, 148 * 16), 128, 0, st>>>(rp, P.col, P.nrows / 3, d_stats + 3, d_same);
+    cudaError_t ce_ = cudaGetLastError();
+    if (ce_ == cudaSuccess) ce_ = cudaMemcpyAsync(h_stats + 3, d_stats + 3, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce_ == cudaSuccess) ce_ = cudaMemcpyAsync(&h_same, d_same, sizeof(h_same), cudaMemcpyDeviceToHost, st);
+    if (ce_ == cudaSuccess) ce_ = cudaStreamSynchronize(st);
+    cudaFree(d_same);
+    PCGB_CUDA(ce_);
+    // node-block kernel only for (mostly) regular node rows: on the octree model (concrete) the row-group kernel measured
+    // faster (0.17 ms against 0.34 ms per SpMV, profiles/bench_r2e_*): irregular tiles need the per-block node search
+    bsr_ok = h_stats[3] == 0 && (double)h_same >= 0.01 * env_int("PCGB_BSR_MIN_UNIFORM_PCT", 75) * (double)(P.nrows / 3);
     h_stats[3] = 0;
   }
   if (bsr_ok) {
     // one 3x3 block per consumer thread and pass (256 threads): a tile of at most 256 (or 512) blocks whatever the node snap does
     const int node_items = 3 * (P.max_row + 1);
-    int t = 2304 - node_items;                             // <= 256 blocks whatever the snap does: one pass of 256 threads
-    if (t < 1536) t = 2304;                                // long node rows (octree meshes): allow a second, partly filled pass
+    // two 3x3 blocks per consumer thread (<= 512 blocks whatever the node snap does) in a 2-stage ring per CTA: the largest
+    // tiles that still leave two CTAs per SM won the B200 sweeps (profiles/spmv_sweep_r2*.txt: 0.82 ms against 1.03 ms for
+    // 256-block tiles in a 4-stage ring and 0.93 ms for the row-group kernel)
+    int t = 4608 - node_items;
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1315,11 +1342,9 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
             const int scratch = 6 * P.cap_blocks * 8 + 2 * (P.cap_nodes + 2) * 4;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
-            int bst = 4, bct = 2;
-            if (2 * (4 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) {
-              if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) <= 227 * 1024) bst = 2;
-              else bct = 1;
-            }
+            int bst = 2, bct = 2;
+            if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
+            P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (env_int("PCGB_BSR_P2", 0) ? 2 : 0);
             bst = env_int("PCGB_SPMV_STAGES", bst);
             bct = env_int("PCGB_SPMV_CTAS", bct);
             if (bst < 1) bst = 1;
@@ -1332,10 +1357,12 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             if (bfit < 1) bfit = 1;
             P.bsr = h_fb == 0 && P.smem_bsr <= 200 * 1024;
             if (P.bsr) {
-              P.persist = true;
-              k_mark_uniform<RP><<<(P.ntiles + 255) / 256, 256, 0, st>>>(rp, P.tile_desc, P.ntiles);
+              // uniform tiles (every node of the tile has the same number of blocks) take the search-free path
+              PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+              k_mark_uniform<RP><<<(P.ntiles + 255) / 256, 256, 0, st>>>(rp, P.tile_desc, P.ntiles, d_fail);
               PCGB_CHECK_LAUNCH();
               PCGB_CUDA(cudaStreamSynchronize(st));
+              P.persist = true;
               P.ctas_per_sm = std::min(bct > 0 ? bct : 1, bfit);
               P.grid_bsr = std::min(P.ntiles, num_sms() * P.ctas_per_sm);
               P.grid_persist = P.grid_bsr; P.smem_persist = P.smem_bsr; P.stages = P.bsr_stages; P.stage_bytes = P.bsr_stage_bytes;
@@ -1463,7 +1490,7 @@ inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStr
   if (ntiles == 0) return PCGB_OK;
   kern<<<grid, (kConsWarps + P.bsr_prod) * 32, P.smem_bsr, st>>>(static_cast<const RP *>(P.rowptr), P.bidx, P.val, x, y, desc, P.win_start,
                                                                   P.win_off, ntiles, P.nnz, P.cap_nnz, P.cap_nodes, P.cap_x, P.cap_blocks,
-                                                                  P.bsr_stages, P.bsr_stage_bytes, dotp, skip);
+                                                                  P.bsr_stages, P.bsr_stage_bytes, P.bsr_mode, dotp, skip);
   PCGB_CHECK_LAUNCH();
   return PCGB_OK;
 }

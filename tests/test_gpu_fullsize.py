@@ -24,8 +24,8 @@ def test_c2_structure(c2):
     blk, A, b = c2
     assert A.shape == (6390144, 6390144) and A.nnz == 509597550          # n and nnz of C2
     info = A.plan_info()
-    assert info["staged"] == 2 and info["split_rows"] == 0 and info["max_row"] == 81
-    assert A.stream_bytes() < 0.85 * A.spmv_bytes()      # 10 B per non-zero (16-bit staged positions) against the contract's 12
+    assert info["staged"] == 2 and info["split_rows"] == 0 and info["max_row"] == 81 and info["index_mode"] == 2
+    assert A.stream_bytes() < 0.71 * A.spmv_bytes()      # node-block kernel: 8 + 2/9 B per non-zero against the contract's 12
 
 
 def test_c2_linearity_symmetry_nullspace(c2):

@@ -228,6 +228,7 @@ def test_spmv_interface_first_split(cuda, monkeypatch, t3):
     from pcg_mpi_solver_b200.csr import CsrMatrix
     monkeypatch.setenv("PCGB_SPMV_T3", "1" if t3 == "1" else "0")
     monkeypatch.setenv("PCGB_SPMV_BSR", "1" if t3 == "bsr" else "0")
+    monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")
     monkeypatch.setenv("PCGB_SPMV_TILE", "512" if t3 != "bsr" else "768")
     A = R.hex_box_csr((12, 10, 8), (0, 0, 0), (12, 10, 8))
     n = A.shape[0]
@@ -275,13 +276,17 @@ def test_release_col(cuda):
         assert not P.release_col() and P.col is not None
 
 
-@pytest.mark.parametrize("tile", [0, 600, 1200, 4300])
-def test_spmv_node_block_kernel(cuda, monkeypatch, tile):
+@pytest.mark.parametrize("mode", [(1, 0), (0, 0), (1, 1)])
+@pytest.mark.parametrize("tile", [0, 600, 1200, 2058])
+def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
     """Node-block ("BSR-3") kernel, the default for 3-dofs-per-node matrices: one thread per 3x3 block, one 16-bit staged position
     per block (8 + 2/9 B per non-zero), rows summed from shared-memory partials in block order.  Several tile sizes (one and
     several passes of 256 blocks, 2- and 4-stage rings), clamped / interior boxes, fused dot, bit-reproducibility."""
     import torch
     from pcg_mpi_solver_b200.csr import CsrMatrix
+    monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")     # small boxes are mostly boundary: do not let the regularity gate decide
+    monkeypatch.setenv("PCGB_BSR_UNI", str(mode[0]))        # uniform-tile fast path on / off
+    monkeypatch.setenv("PCGB_BSR_P2", str(mode[1]))         # row sums: one thread per row / 8 lanes per row
     if tile:
         monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     for box in [((9, 7, 5), (0, 0, 0), (9, 7, 5)), ((8, 6, 4), (4, 0, 2), (4, 3, 2)), ((14, 12, 10), (0, 0, 0), (14, 12, 10))]:
@@ -300,8 +305,12 @@ def test_spmv_node_block_kernel(cuda, monkeypatch, tile):
         assert abs(float(d) - ref) <= 1e-12 * float(torch.dot(x.abs(), y.abs()))
 
 
-def test_spmv_node_block_irregular_nodes(cuda):
-    """Nodes with different numbers of blocks per row (a random node graph expanded to 3x3 blocks) - the octree / concrete shape."""
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_spmv_node_block_irregular_nodes(cuda, monkeypatch, mode):
+    """Nodes with different numbers of blocks per row (a random node graph expanded to 3x3 blocks) - the octree / concrete shape.
+    Such matrices stay on the row-group kernel by default (regularity gate); forced here to cover the per-block node search."""
+    monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")
+    monkeypatch.setenv("PCGB_BSR_P2", mode)
     rng = np.random.default_rng(12)
     nn = 700
     rows, cols = [], []
@@ -322,3 +331,6 @@ def test_spmv_node_block_irregular_nodes(cuda):
     B = B.tocsr(); B.eliminate_zeros(); B.sort_indices()
     M = _check_spmv(B, cuda, seed=5)
     assert M.plan_info()["index_mode"] == 0
+    # default gate: an irregular node graph is not sent to the node-block kernel
+    monkeypatch.delenv("PCGB_BSR_MIN_UNIFORM_PCT")
+    assert _check_spmv(A, cuda, seed=6).plan_info()["index_mode"] == 0
