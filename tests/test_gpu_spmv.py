@@ -276,7 +276,7 @@ def test_release_col(cuda):
         assert not P.release_col() and P.col is not None
 
 
-@pytest.mark.parametrize("mode", [(1, 0), (0, 0), (1, 1)])
+@pytest.mark.parametrize("mode", [(1, 0, 1), (0, 0, 1), (1, 0, 0), (0, 0, 0), (1, 1, 0)])
 @pytest.mark.parametrize("tile", [0, 600, 1200, 2058])
 def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
     """Node-block ("BSR-3") kernel, the default for 3-dofs-per-node matrices: one thread per 3x3 block, one 16-bit staged position
@@ -287,6 +287,7 @@ def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
     monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")     # small boxes are mostly boundary: do not let the regularity gate decide
     monkeypatch.setenv("PCGB_BSR_UNI", str(mode[0]))        # uniform-tile fast path on / off
     monkeypatch.setenv("PCGB_BSR_P2", str(mode[1]))         # row sums: one thread per row / 8 lanes per row
+    monkeypatch.setenv("PCGB_BSR_SEG", str(mode[2]))        # warp-segmented partials (default) / one partial triple per block
     if tile:
         monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     for box in [((9, 7, 5), (0, 0, 0), (9, 7, 5)), ((8, 6, 4), (4, 0, 2), (4, 3, 2)), ((14, 12, 10), (0, 0, 0), (14, 12, 10))]:
@@ -305,12 +306,14 @@ def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
         assert abs(float(d) - ref) <= 1e-12 * float(torch.dot(x.abs(), y.abs()))
 
 
-@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("mode", ["seg", "0", "1"])
 def test_spmv_node_block_irregular_nodes(cuda, monkeypatch, mode):
     """Nodes with different numbers of blocks per row (a random node graph expanded to 3x3 blocks) - the octree / concrete shape.
     Such matrices stay on the row-group kernel by default (regularity gate); forced here to cover the per-block node search."""
     monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")
-    monkeypatch.setenv("PCGB_BSR_P2", mode)
+    monkeypatch.setenv("PCGB_BSR_SEG", "1" if mode == "seg" else "0")
+    monkeypatch.setenv("PCGB_BSR_P2", "0" if mode == "seg" else mode)
+    monkeypatch.setenv("PCGB_SPMV_TILE", "1500")           # random columns: one x window per block - stay below the 256-window budget
     rng = np.random.default_rng(12)
     nn = 700
     rows, cols = [], []
@@ -333,4 +336,5 @@ def test_spmv_node_block_irregular_nodes(cuda, monkeypatch, mode):
     assert M.plan_info()["index_mode"] == 0
     # default gate: an irregular node graph is not sent to the node-block kernel
     monkeypatch.delenv("PCGB_BSR_MIN_UNIFORM_PCT")
+    monkeypatch.delenv("PCGB_SPMV_TILE")
     assert _check_spmv(A, cuda, seed=6).plan_info()["index_mode"] == 0

@@ -10,13 +10,14 @@ blk = HexBlock((blk_n,) * 3, (0, 0, 0), (blk_n,) * 3, h=1.0 / blk_n)
 base = generate_matrix(blk, device=dev)
 x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
-BSR = {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2}
+BSR = {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_CTAS": 2}
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or [
     {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
-    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_BSR_UNI": u, "PCGB_BSR_P2": p2} for t in (4362, 3900) for (u, p2) in ((1, 0), (0, 0), (1, 1), (0, 1))],
-    {**BSR, "PCGB_SPMV_TILE": 4440, "PCGB_BSR_UNI": 1, "PCGB_BSR_P2": 0},
-    {**BSR, "PCGB_SPMV_TILE": 4200, "PCGB_BSR_UNI": 1, "PCGB_BSR_P2": 0},
-    {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2, "PCGB_SPMV_TILE": 2058, "PCGB_BSR_UNI": 1, "PCGB_BSR_P2": 0}]
+    {**BSR, "PCGB_SPMV_TILE": 4362, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 0},
+    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 1} for t in (4362, 4900, 5150, 5386, 5500)],
+    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 3, "PCGB_BSR_SEG": 1} for t in (3000, 3400, 3650)],
+    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_BSR_SEG": 1} for t in (2058, 2700)],
+    {**BSR, "PCGB_SPMV_TILE": 5386, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 1, "PCGB_BSR_UNI": 0}]
 for cfg in configs:
     for k, v in cfg.items():
         os.environ[k] = str(v)
