@@ -808,10 +808,10 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
   // stage layout: sval[cap_nnz] f64 | sx[cap_x] f64 | snp[cap_nodes+2] i64 | sbidx[cap_blocks+16] u16 | meta[8] i32
   const size_t off_sx = (size_t)cap_nnz * 8, off_snp = off_sx + (size_t)cap_x * 8;
   const size_t off_sb = off_snp + (size_t)(cap_nodes + 2) * 8, off_meta = (off_sb + (size_t)(cap_blocks + 16) * 2 + 15) & ~(size_t)15;
-  // scratch behind the stages: row partials [2][part_len] f64 (3 per block, or - mode bit 2 - 3 per (warp pass, node) segment),
-  // node block offsets [2][cap_nodes+2] i32
-  const bool seg = (mode & 4) != 0;
-  const int part_len = seg ? 3 * (cap_blocks / 32 + cap_nodes + 4) : 3 * cap_blocks;
+  // scratch behind the stages: row partials [2][3*cap_blocks] f64, node block offsets [2][cap_nodes+2] i32
+  // (tried and rejected on B200, profiles/spmv_sweep_r2g.txt: a warp-segmented scan that leaves only a few partials per tile -
+  //  no 25 KB scratch, larger stages - but 35 shuffles per pass: 1.04 ms against 0.86 ms; 8 lanes per row in phase 2: 0.91 ms)
+  const int part_len = 3 * cap_blocks;
   double *spart = reinterpret_cast<double *>(smem_raw + (size_t)stages * stage_bytes);
   int *snbo = reinterpret_cast<int *>(spart + (size_t)2 * part_len);
 
@@ -922,69 +922,11 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     const uint16_t *sbt = sb + meta[6];
     const double *svt = sval + k0l;
     // uniform tile (all nodes have the same number of blocks - the interior of a structured mesh): node = b / Lb, no look-ups
-    const bool uni = (mode & 1) != 0 && meta[7] != 0 && NN > 0;
+    const bool uni = (mode & 1) != 0 && meta[7] != 0 && NN > 0 && NB >= 2 * NN;   // (>= 2 blocks per node: the reciprocal fits 32 bits)
     const int Lbu = uni ? NB / NN : 0;
     const unsigned magic = uni ? (unsigned)((0xffffffffull + (unsigned)Lbu) / (unsigned)Lbu) : 0u;   // b / Lbu = (b * magic) >> 32 for b < 2^16
     // block offset of every node (kept for phase 2, which runs after the stage has been handed back)
     for (int i = tid; i <= NN; i += NT) nbo[i] = uni ? i * Lbu : (int)((int64_t)snp[i] - k0) / 9;
-    if (seg) {
-      // ---- phase 1 (mode bit 2): products, then a warp-segmented scan by node (node ids ascend with the lane): only the
-      //      last lane of every (warp pass, node) segment writes - a handful of partials per tile instead of 3 per block
-      for (int bp = 0; bp < NB; bp += NT) {          // CTA-uniform trip count (full-mask shuffles)
-        const int b = bp + tid;
-        const bool live = b < NB;
-        int i = NN;                                  // sentinel: its own segment
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-        if (live) {
-          int noff, L, t3;
-          if (uni) {
-            i = (int)__umulhi((unsigned)b, magic);
-            noff = i * 9 * Lbu; L = 3 * Lbu; t3 = 3 * (b - i * Lbu);
-          } else {
-            int lo = 0, hi = NN - 1;
-            const int kb = 9 * b;
-            while (lo < hi) {
-              const int mid = (lo + hi + 1) >> 1;
-              if ((int)((int64_t)snp[mid] - k0) <= kb) lo = mid; else hi = mid - 1;
-            }
-            i = lo;
-            noff = (int)((int64_t)snp[lo] - k0);
-            L = ((int)((int64_t)snp[lo + 1] - k0) - noff) / 3;
-            t3 = (kb - noff) / 3;
-          }
-          const int ii = sbt[b];
-          const double *pv = svt + noff + t3;
-          const double x0 = sx[ii], x1 = sx[ii + 1], x2 = sx[ii + 2];
-          p0 = fma(pv[2], x2, fma(pv[1], x1, pv[0] * x0));
-          p1 = fma(pv[L + 2], x2, fma(pv[L + 1], x1, pv[L] * x0));
-          p2 = fma(pv[2 * L + 2], x2, fma(pv[2 * L + 1], x1, pv[2 * L] * x0));
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int in = __shfl_up_sync(0xffffffffu, i, d);
-          const double q0 = __shfl_up_sync(0xffffffffu, p0, d), q1 = __shfl_up_sync(0xffffffffu, p1, d), q2 = __shfl_up_sync(0xffffffffu, p2, d);
-          if (lane >= d && in == i) { p0 += q0; p1 += q1; p2 += q2; }
-        }
-        const int inext = __shfl_down_sync(0xffffffffu, i, 1);
-        if (live && (lane == 31 || inext != i)) {    // tail of the segment: slot (warp pass + node) is unique along the tile
-          double *sp = part + 3 * ((b >> 5) + i);
-          sp[0] = p0; sp[1] = p1; sp[2] = p2;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      named_bar_sync(1, NT);
-      for (int r = tid; r < R; r += NT) {            // phase 2: a row adds the partials of the warp passes its node spans
-        const int i = r / 3, k = r - 3 * i;
-        const int b0 = nbo[i], b1 = nbo[i + 1];
-        double acc = 0.0;
-        if (b1 > b0)
-          for (int w = b0 >> 5; w <= ((b1 - 1) >> 5); ++w) acc += part[3 * (w + i) + k];
-        y[r0 + r] = acc;
-        if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
-      }
-      continue;
-    }
     // ---- phase 1: one 3x3 block per thread and pass
     for (int b = tid; b < NB; b += NT) {
       int noff, L, t3;
@@ -1016,37 +958,15 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);     // the stage is free: everything phase 2 needs is in the scratch
     named_bar_sync(1, NT);
-    if ((mode & 2) == 0) {
-      // ---- phase 2 (default): one row per thread, partials added in block order.  Only the first warp(s) are busy here; the
-      //      others already wait for / start on the next tile, so this overlaps with the next phase 1.
-      for (int r = tid; r < R; r += NT) {
-        const int i = r / 3, k = r - 3 * i;
-        const int b0 = nbo[i], b1 = nbo[i + 1];
-        double acc = 0.0;
-        for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
-        y[r0 + r] = acc;
-        if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
-      }
-      continue;
-    }
-    // ---- phase 2 (mode bit 1): 8 lanes per row, each adds a contiguous run of the row's partials, then a fixed shuffle tree
-    for (int rb = 0; rb < R; rb += NT / 8) {         // warp-uniform trip count (full-mask shuffles)
-      const int r = rb + (tid >> 3), j = tid & 7;
-      const bool live = r < R;
+    // ---- phase 2: one row per thread, partials added in block order.  Only the first warp(s) are busy here; the others
+    //      already wait for / start on the next tile, so this overlaps with the next phase 1.
+    for (int r = tid; r < R; r += NT) {
+      const int i = r / 3, k = r - 3 * i;
+      const int b0 = nbo[i], b1 = nbo[i + 1];
       double acc = 0.0;
-      if (live) {
-        const int i = r / 3, k = r - 3 * i;
-        const int b0 = nbo[i], nblk = nbo[i + 1] - b0;
-        const int chunk = (nblk + 7) >> 3;
-        int lo = b0 + j * chunk, hi = lo + chunk;
-        if (hi > b0 + nblk) hi = b0 + nblk;
-        for (int b = lo; b < hi; ++b) acc += part[3 * b + k];
-      }
-      acc = group_sum<8>(acc);
-      if (live && j == 0) {
-        y[r0 + r] = acc;
-        if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
-      }
+      for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
+      y[r0 + r] = acc;
+      if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
     }
   }
   if (DOT) {
@@ -1239,7 +1159,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
     // two 3x3 blocks per consumer thread (<= 512 blocks whatever the node snap does) in a 2-stage ring per CTA: the largest
     // tiles that still leave two CTAs per SM won the B200 sweeps (profiles/spmv_sweep_r2*.txt: 0.82 ms against 1.03 ms for
     // 256-block tiles in a 4-stage ring and 0.93 ms for the row-group kernel)
-    int t = (env_int("PCGB_BSR_SEG", 1) ? 5632 : 4608) - node_items;   // warp-segmented sums need no per-block scratch: larger stages
+    int t = 4608 - node_items;
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1401,9 +1321,8 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             P.cap_nodes = (P.cap_rows / 3 + 2 + 1) & ~1;
             P.bsr_stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + (P.cap_nodes + 2) * 8 + (((P.cap_blocks + 16) * 2 + 15) & ~15) + 32;
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
-            P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (env_int("PCGB_BSR_P2", 0) ? 2 : 0) | (env_int("PCGB_BSR_SEG", 1) ? 4 : 0);
-            const int part_len = (P.bsr_mode & 4) ? 3 * (P.cap_blocks / 32 + P.cap_nodes + 4) : 3 * P.cap_blocks;
-            const int scratch = 2 * part_len * 8 + 2 * (P.cap_nodes + 2) * 4;
+            P.bsr_mode = env_int("PCGB_BSR_UNI", 1) ? 1 : 0;
+            const int scratch = 6 * P.cap_blocks * 8 + 2 * (P.cap_nodes + 2) * 4;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
             if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }

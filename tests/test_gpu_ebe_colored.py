@@ -1,5 +1,5 @@
-"""ROUND-2 PREPARATION: coloured (atomics-free, deterministic) EBE operator.  Written at the end of round 1 with no
-GPU time left; runs only with PCGB_EXPERIMENTAL=1 so that unverified kernels cannot disturb the verified suite."""
+"""Coloured (atomics-free, bit-reproducible) variant of the matrix-free EBE operator (csrc/ebe_color.cuh): the
+deterministic counterpart of np.bincount's scatter-add (pcg_solver.py:300).  First run on a B200 in round 2 (both tests green)."""
 import os
 
 import numpy as np
@@ -7,8 +7,7 @@ import pytest
 
 from oracle.hex_mdf import write_hex_mdf
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PCGB_EXPERIMENTAL") != "1", reason="unverified round-2 preparation (PCGB_EXPERIMENTAL=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_colored_ebe_matches_csr_and_is_bit_reproducible(cuda, tmp_path):

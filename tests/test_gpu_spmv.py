@@ -276,23 +276,21 @@ def test_release_col(cuda):
         assert not P.release_col() and P.col is not None
 
 
-@pytest.mark.parametrize("mode", [(1, 0, 1), (0, 0, 1), (1, 0, 0), (0, 0, 0), (1, 1, 0)])
+@pytest.mark.parametrize("uni", [1, 0])
 @pytest.mark.parametrize("tile", [0, 600, 1200, 2058])
-def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
+def test_spmv_node_block_kernel(cuda, monkeypatch, tile, uni):
     """Node-block ("BSR-3") kernel, the default for 3-dofs-per-node matrices: one thread per 3x3 block, one 16-bit staged position
     per block (8 + 2/9 B per non-zero), rows summed from shared-memory partials in block order.  Several tile sizes (one and
     several passes of 256 blocks, 2- and 4-stage rings), clamped / interior boxes, fused dot, bit-reproducibility."""
     import torch
     from pcg_mpi_solver_b200.csr import CsrMatrix
     monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")     # small boxes are mostly boundary: do not let the regularity gate decide
-    monkeypatch.setenv("PCGB_BSR_UNI", str(mode[0]))        # uniform-tile fast path on / off
-    monkeypatch.setenv("PCGB_BSR_P2", str(mode[1]))         # row sums: one thread per row / 8 lanes per row
-    monkeypatch.setenv("PCGB_BSR_SEG", str(mode[2]))        # warp-segmented partials (default) / one partial triple per block
+    monkeypatch.setenv("PCGB_BSR_UNI", str(uni))            # uniform-tile fast path on / off (off: per-block node search everywhere)
     if tile:
         monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     for box in [((9, 7, 5), (0, 0, 0), (9, 7, 5)), ((8, 6, 4), (4, 0, 2), (4, 3, 2)), ((14, 12, 10), (0, 0, 0), (14, 12, 10))]:
         A = R.hex_box_csr(*box)
-        M = _check_spmv(A, cuda, seed=tile)
+        M = _check_spmv(A, cuda, seed=tile + uni)
         info = M.plan_info()
         assert info["index_mode"] == 2 and info["staged"] == 2 and info["split_rows"] == 0, info
         assert M.stream_bytes() < 8.3 * A.nnz + 40 * A.shape[0] + 64 * info["ntiles"]
@@ -306,13 +304,10 @@ def test_spmv_node_block_kernel(cuda, monkeypatch, tile, mode):
         assert abs(float(d) - ref) <= 1e-12 * float(torch.dot(x.abs(), y.abs()))
 
 
-@pytest.mark.parametrize("mode", ["seg", "0", "1"])
-def test_spmv_node_block_irregular_nodes(cuda, monkeypatch, mode):
+def test_spmv_node_block_irregular_nodes(cuda, monkeypatch):
     """Nodes with different numbers of blocks per row (a random node graph expanded to 3x3 blocks) - the octree / concrete shape.
     Such matrices stay on the row-group kernel by default (regularity gate); forced here to cover the per-block node search."""
     monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")
-    monkeypatch.setenv("PCGB_BSR_SEG", "1" if mode == "seg" else "0")
-    monkeypatch.setenv("PCGB_BSR_P2", "0" if mode == "seg" else mode)
     monkeypatch.setenv("PCGB_SPMV_TILE", "1500")           # random columns: one x window per block - stay below the 256-window budget
     rng = np.random.default_rng(12)
     nn = 700

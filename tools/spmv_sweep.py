@@ -6,18 +6,28 @@ from pcg_mpi_solver_b200.hexmesh import HexBlock, generate_matrix
 from pcg_mpi_solver_b200.csr import CsrMatrix
 blk_n = int(os.environ.get("SWEEP_BLOCK", "128"))
 dev = torch.device("cuda:0")
-blk = HexBlock((blk_n,) * 3, (0, 0, 0), (blk_n,) * 3, h=1.0 / blk_n)
-base = generate_matrix(blk, device=dev)
+if os.environ.get("SWEEP_MODEL", "hex") == "concrete":
+    # the irregular octree model (config C4, one part): 616 413 rows, 24..324 non-zeros per row
+    from pcg_mpi_solver_b200.partition import assemble_csr_device, partition_mesh
+    sub = partition_mesh(os.path.join("oracle", "_ref", "concrete.zip"), 1, assemble=False)[0]
+    rp, col, val = assemble_csr_device(sub, dev)
+    base = CsrMatrix(rp, col, val, (sub.n, sub.n))
+else:
+    blk = HexBlock((blk_n,) * 3, (0, 0, 0), (blk_n,) * 3, h=1.0 / blk_n)
+    base = generate_matrix(blk, device=dev)
 x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
-BSR = {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_CTAS": 2}
-configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or [
-    {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
-    {**BSR, "PCGB_SPMV_TILE": 4362, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 0},
-    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 1} for t in (4362, 4900, 5150, 5386, 5500)],
-    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 3, "PCGB_BSR_SEG": 1} for t in (3000, 3400, 3650)],
-    *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_BSR_SEG": 1} for t in (2058, 2700)],
-    {**BSR, "PCGB_SPMV_TILE": 5386, "PCGB_SPMV_STAGES": 2, "PCGB_BSR_SEG": 1, "PCGB_BSR_UNI": 0}]
+BSR = {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_CTAS": 2, "PCGB_SPMV_STAGES": 2}
+if os.environ.get("SWEEP_MODEL", "hex") == "concrete":
+    default = [{"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for l in (8, 16, 32) for t in (1536, 1792, 2048, 2304)] + [
+        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1280, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3},
+        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1792, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2, "PCGB_SPMV_GAP": 32},
+        {"PCGB_BSR_MIN_UNIFORM_PCT": 0, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2}]
+else:
+    default = [
+        {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
+        *[{**BSR, "PCGB_SPMV_TILE": t} for t in (4200, 4362, 4440)]]
+configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
     for k, v in cfg.items():
         os.environ[k] = str(v)
