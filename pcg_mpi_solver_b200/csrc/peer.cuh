@@ -10,9 +10,10 @@
 //                spins (ld.acquire.sys) until all nranks slots of its own window carry the epoch, adds them in rank
 //                order (bit-identical on every rank) and runs the scalar PCG logic - one launch, no NCCL kernel;
 //   halo         k_halo_pack_peer gathers the interface values and stores them into the neighbours' receive buffers
-//                (the last CTA to finish releases one flag per neighbour); the stores travel while the interior tiles
-//                of the SpMV run; k_halo_unpack_peer acquires the flags and adds in neighbour order (the
-//                reference's summation order, pcg_solver.py:332-334; deterministic).
+//                (the last CTA to finish releases one flag per neighbour); k_halo_unpack_peer acquires the flags and
+//                adds in neighbour order (the reference's summation order, pcg_solver.py:332-334; deterministic).  In
+//                the PCG loop the unpack runs on a forked stream beside the p.q all-reduce (both only wait for remote
+//                data); an optional interface-first split of the SpMV can put the interior tiles behind the pack.
 //
 // Epochs come from device memory (graph replays need no new kernel arguments); buffers are double-buffered by the
 // epoch parity, which is enough because a rank can run at most one exchange ahead of its slowest peer (every exchange
@@ -190,7 +191,7 @@ k_halo_pack_peer(PeerHalo h, const int *__restrict__ idx, const double *__restri
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  // (the release store orders everything this thread has observed - the other CTAs' fenced stores through the counter - first)
   if ((int)threadIdx.x < h.n_nbr) st_release_sys(h.remote_flag[threadIdx.x] + par, ep);
   if (threadIdx.x == 0) { *h.done = 0; *h.epoch = ep; }
 }
