@@ -220,3 +220,48 @@ def test_hex_solve_c2_small(cuda):
     ref13 = _oracle(As, b.cpu().numpy(), 1.0 / As.diagonal(), 1e-13, 5000)
     x13 = solve(op, b, minv, 1e-13, 5000)[0]
     assert np.linalg.norm(x13.cpu().numpy() - ref13["X"][0]) <= 1e-9 * np.linalg.norm(ref13["X"][0])
+
+
+def test_two_host_threads_two_solvers(cuda):
+    """Re-entrancy of the C ABI ("re-entrant per handle, no global state besides last-error TLS"): two host threads,
+    each with its own matrix / solver handle (ctypes releases the GIL during the calls), solve different systems at the
+    same time; results are bit-identical to the same solves run one after the other.  pcgb_dot_w (stream-ordered scratch) too."""
+    import threading
+
+    import torch
+    from pcg_mpi_solver_b200 import _lib, solve
+    from pcg_mpi_solver_b200.csr import CsrMatrix
+    from pcg_mpi_solver_b200.solver import SubdomainOperator
+    systems = []
+    for seed, A in ((1, R.hex_box_csr((10, 8, 6), (0, 0, 0), (10, 8, 6))), (2, R.poisson27(14))):
+        b = np.random.default_rng(seed).standard_normal(A.shape[0])
+        systems.append((A, b, 1.0 / A.diagonal()))
+    serial = [solve(A, b, m, 1e-11, 3000) for A, b, m in systems]
+    ops = [SubdomainOperator(CsrMatrix.from_scipy(A, device=cuda)) for A, _, _ in systems]
+    out, errs = [None, None], []
+
+    def work(k):
+        try:
+            A, b, m = systems[k]
+            s = torch.cuda.Stream(device=cuda)
+            with torch.cuda.stream(s):
+                bd, md = torch.from_numpy(b).to(cuda), torch.from_numpy(m).to(cuda)
+                for _ in range(5):                                   # several solves per thread: graphs, buffers and scratch are per handle
+                    x, info = ops[k].solve(bd, md, 1e-11, 3000)
+                d = torch.zeros(1, dtype=torch.float64, device=cuda)
+                _lib.check(_lib.load().pcgb_dot_w(bd.numel(), _lib.ptr(bd), _lib.ptr(bd), None, _lib.ptr(d), s.cuda_stream))
+                s.synchronize()
+                out[k] = (x.cpu().numpy(), info.flag, info.relres, info.iters, float(d))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for k in range(2):
+        x, flag, relres, iters, d = out[k]
+        assert (flag, relres, iters) == serial[k][1:] and np.array_equal(x, serial[k][0])
+        assert abs(d - float(systems[k][1] @ systems[k][1])) <= 1e-12 * d
