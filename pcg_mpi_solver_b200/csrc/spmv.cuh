@@ -1095,11 +1095,19 @@ inline int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+// device temporaries of the plan builder: freed on every exit path (the PCGB_CUDA macro returns early on errors)
+struct DevTmp {
+  void *p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
 template <typename RP>
 inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   const RP *rp = static_cast<const RP *>(P.rowptr);
-  int *d_stats = nullptr;
-  PCGB_CUDA(cudaMalloc(&d_stats, 4 * sizeof(int)));
+  DevTmp t_stats, t_head;
+  PCGB_CUDA(cudaMalloc(&t_stats.p, 4 * sizeof(int)));
+  int *const d_stats = t_stats.as<int>();
   PCGB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(int), st));
   if (P.nrows > 0) {
     int grid = (int)std::min<int64_t>((P.nrows + 255) / 256, 148 * 8);
@@ -1176,8 +1184,8 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   PCGB_CUDA(cudaMalloc(&P.carry, (size_t)P.ntiles * sizeof(double)));
   PCGB_CUDA(cudaMalloc(&P.dot_partials, (size_t)P.ntiles * sizeof(double)));
   PCGB_CUDA(cudaMemsetAsync(P.carry, 0, (size_t)P.ntiles * sizeof(double), st));
-  unsigned char *d_head = nullptr;
-  PCGB_CUDA(cudaMalloc(&d_head, (size_t)P.ntiles));
+  PCGB_CUDA(cudaMalloc(&t_head.p, (size_t)P.ntiles));
+  unsigned char *const d_head = t_head.as<unsigned char>();
   k_partition<RP><<<(P.ntiles + 1 + 255) / 256, 256, 0, st>>>(rp, P.nrows, P.nnz, P.tile_items, P.ntiles, P.snap ? 1 : 0,
                                                                P.tile_row, P.tile_k, bsr_ok ? 3 : 1);
   PCGB_CHECK_LAUNCH();
@@ -1223,10 +1231,12 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
   if (P.use_tma && P.nnz > 0 && env_int("PCGB_SPMV_STAGE", 1) != 0) {
     const int gap = env_int("PCGB_SPMV_GAP", 8);
     const int plan_smem = (P.cap_nnz + 3 * kMaxRuns + 2 * kMaxWin + 8) * (int)sizeof(int);
-    int *d_fail = nullptr, *d_nw = nullptr;
-    PCGB_CUDA(cudaMalloc(&d_fail, sizeof(int)));
+    DevTmp t_fail, t_nw;
+    PCGB_CUDA(cudaMalloc(&t_fail.p, sizeof(int)));
+    int *const d_fail = t_fail.as<int>();
     PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
-    PCGB_CUDA(cudaMalloc(&d_nw, (size_t)P.ntiles * sizeof(int)));
+    PCGB_CUDA(cudaMalloc(&t_nw.p, (size_t)P.ntiles * sizeof(int)));
+    int *const d_nw = t_nw.as<int>();
     PCGB_CUDA(cudaMalloc(&P.tile_xlen, (size_t)P.ntiles * sizeof(int)));
     PCGB_CUDA(cudaFuncSetAttribute(k_plan_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, plan_smem));
     k_plan_windows<<<P.ntiles, 256, plan_smem, st>>>(P.col, P.tile_k, P.cap_nnz, gap, 1, nullptr, nullptr, nullptr, nullptr, d_nw,
@@ -1370,16 +1380,12 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
         }
       }
     }
-    cudaFree(d_fail);
-    cudaFree(d_nw);
     if (!P.staged) {
       P.persist = false;
       cudaFree(P.tile_xlen); cudaFree(P.tile_win); cudaFree(P.win_start); cudaFree(P.win_off); cudaFree(P.lidx);
       P.tile_xlen = nullptr; P.tile_win = nullptr; P.win_start = nullptr; P.win_off = nullptr; P.lidx = nullptr;
     }
   }
-  cudaFree(d_head);
-  cudaFree(d_stats);
   return spmv_configure(P);
 }
 
