@@ -811,7 +811,11 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
   // scratch behind the stages: row partials [2][3*cap_blocks] f64, node block offsets [2][cap_nodes+2] i32
   // (tried and rejected on B200, profiles/spmv_sweep_r2g.txt: a warp-segmented scan that leaves only a few partials per tile -
   //  no 25 KB scratch, larger stages - but 35 shuffles per pass: 1.04 ms against 0.86 ms; 8 lanes per row in phase 2: 0.91 ms)
-  const int part_len = 3 * cap_blocks;
+  // mode bit 1 (default): the row partials of a block OVERWRITE the block's own first-row values in the stage (the thread has all
+  // nine values in registers by then) - no separate scratch, which buys a third stage per CTA; the stage is handed back to
+  // the producer only after phase 2 has read the partials.
+  const bool inplace = (mode & 2) != 0;
+  const int part_len = inplace ? 0 : 3 * cap_blocks;
   double *spart = reinterpret_cast<double *>(smem_raw + (size_t)stages * stage_bytes);
   int *snbo = reinterpret_cast<int *>(spart + (size_t)2 * part_len);
 
@@ -950,13 +954,16 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
       const double a0 = pv[0], a1 = pv[1], a2 = pv[2];
       const double b0 = pv[L], b1 = pv[L + 1], b2 = pv[L + 2];
       const double c0 = pv[2 * L], c1 = pv[2 * L + 1], c2 = pv[2 * L + 2];
-      double *pp = part + 3 * b;
+      double *pp = inplace ? const_cast<double *>(pv) : part + 3 * b;   // in place: positions 3t..3t+2 of the node's first row
       pp[0] = fma(a2, x2, fma(a1, x1, a0 * x0));
       pp[1] = fma(b2, x2, fma(b1, x1, b0 * x0));
       pp[2] = fma(c2, x2, fma(c1, x1, c0 * x0));
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);     // the stage is free: everything phase 2 needs is in the scratch
+    const bool has_rows = warp * 32 < R;            // this warp owns rows in phase 2
+    if (!inplace || !has_rows) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);   // nothing more to read from the stage for this warp
+    }
     named_bar_sync(1, NT);
     // ---- phase 2: one row per thread, partials added in block order.  Only the first warp(s) are busy here; the others
     //      already wait for / start on the next tile, so this overlaps with the next phase 1.
@@ -964,9 +971,19 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
       const int i = r / 3, k = r - 3 * i;
       const int b0 = nbo[i], b1 = nbo[i + 1];
       double acc = 0.0;
-      for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
+      if (inplace) {
+        const double *pr = svt + 9 * b0 + k;       // first row of node i: partial k of block t at 3 t + k
+        for (int t = 0; t < b1 - b0; ++t) acc += pr[3 * t];
+      } else {
+        for (int b = b0; b < b1; ++b) acc += part[3 * b + k];
+      }
       y[r0 + r] = acc;
       if (DOT) dsum = fma(acc, __ldg(x + r0 + r), dsum);
+    }
+    if (inplace && has_rows) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes to the stage before the next TMA fill
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
   if (DOT) {
@@ -1167,7 +1184,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
     // two 3x3 blocks per consumer thread (<= 512 blocks whatever the node snap does) in a 2-stage ring per CTA: the largest
     // tiles that still leave two CTAs per SM won the B200 sweeps (profiles/spmv_sweep_r2*.txt: 0.82 ms against 1.03 ms for
     // 256-block tiles in a 4-stage ring and 0.93 ms for the row-group kernel)
-    int t = 4608 - node_items;
+    int t = (env_int("PCGB_BSR_INPLACE", 1) != 0 ? 4150 : 4608) - node_items;   // in place: three stages of ~36 KB per CTA
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1331,11 +1348,13 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             P.cap_nodes = (P.cap_rows / 3 + 2 + 1) & ~1;
             P.bsr_stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + (P.cap_nodes + 2) * 8 + (((P.cap_blocks + 16) * 2 + 15) & ~15) + 32;
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
-            P.bsr_mode = env_int("PCGB_BSR_UNI", 1) ? 1 : 0;
-            const int scratch = 6 * P.cap_blocks * 8 + 2 * (P.cap_nodes + 2) * 4;
+            const bool inplace = env_int("PCGB_BSR_INPLACE", 1) != 0;
+            P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (inplace ? 2 : 0);
+            const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
-            if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
+            if (2 * (3 * P.bsr_stage_bytes + scratch + 2048) <= 227 * 1024) bst = 3;       // in-place partials leave room for a third stage
+            else if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
             bst = env_int("PCGB_SPMV_STAGES", bst);
             bct = env_int("PCGB_SPMV_CTAS", bct);
             if (bst < 1) bst = 1;
