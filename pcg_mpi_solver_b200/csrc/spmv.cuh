@@ -1184,7 +1184,9 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
     // two 3x3 blocks per consumer thread (<= 512 blocks whatever the node snap does) in a 2-stage ring per CTA: the largest
     // tiles that still leave two CTAs per SM won the B200 sweeps (profiles/spmv_sweep_r2*.txt: 0.82 ms against 1.03 ms for
     // 256-block tiles in a 4-stage ring and 0.93 ms for the row-group kernel)
-    int t = (env_int("PCGB_BSR_INPLACE", 1) != 0 ? 4150 : 4608) - node_items;   // in place: three stages of ~36 KB per CTA
+    // in-place row partials (default): no scratch, so two stages of ~53 KB per CTA, two CTAs per SM - the largest tiles won
+    // every B200 sweep (profiles/spmv_sweep_r2k.txt: 0.80 ms at 5600 items against 0.86 ms at 4362 with a separate scratch)
+    int t = (env_int("PCGB_BSR_INPLACE", 1) != 0 ? 5632 : 4608) - node_items;
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1353,8 +1355,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
-            if (2 * (3 * P.bsr_stage_bytes + scratch + 2048) <= 227 * 1024) bst = 3;       // in-place partials leave room for a third stage
-            else if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
+            if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
             bst = env_int("PCGB_SPMV_STAGES", bst);
             bct = env_int("PCGB_SPMV_CTAS", bct);
             if (bst < 1) bst = 1;
