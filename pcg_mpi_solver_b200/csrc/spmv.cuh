@@ -1112,6 +1112,8 @@ inline int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+inline void free_plan(CsrPlan &P);
+
 // device temporaries of the plan builder: freed on every exit path (the PCGB_CUDA macro returns early on errors)
 struct DevTmp {
   void *p = nullptr;
@@ -1120,7 +1122,7 @@ struct DevTmp {
 };
 
 template <typename RP>
-inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
+inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attempt = 0) {
   const RP *rp = static_cast<const RP *>(P.rowptr);
   DevTmp t_stats, t_head;
   PCGB_CUDA(cudaMalloc(&t_stats.p, 4 * sizeof(int)));
@@ -1186,7 +1188,9 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
     // 256-block tiles in a 4-stage ring and 0.93 ms for the row-group kernel)
     // in-place row partials (default): no scratch, so two stages of ~53 KB per CTA, two CTAs per SM - the largest tiles won
     // every B200 sweep (profiles/spmv_sweep_r2k.txt: 0.80 ms at 5600 items against 0.86 ms at 4362 with a separate scratch)
-    int t = (env_int("PCGB_BSR_INPLACE", 1) != 0 ? 5632 : 4608) - node_items;
+    // The tile is made as large as two CTAs per SM allow: start high and shrink by 4 % (re-plan) until the ring fits.
+    int t = (env_int("PCGB_BSR_INPLACE", 1) != 0 ? 6100 : 4608) - node_items;
+    if (bsr_tile > 0) t = bsr_tile;
     if (t < 2 * node_items) bsr_ok = false;                // rows too long for node-aligned tiles
     else P.tile_items = env_int("PCGB_SPMV_TILE", t);
     if (bsr_ok && P.tile_items < 2 * node_items) bsr_ok = false;
@@ -1355,7 +1359,19 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st) {
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
-            if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) { bst = 4; bct = 1; }
+            if (2 * (2 * P.bsr_stage_bytes + scratch + 2048) > 227 * 1024) {
+              if (h_fb == 0 && attempt < 8 && env_int("PCGB_SPMV_TILE", 0) == 0 && P.tile_items > 1536) {
+                // two CTAs of two stages do not fit: plan again with a smaller tile (set-up cost only)
+                const int smaller = (int)(P.tile_items * 0.96) & ~1;
+                const void *rowptr = P.rowptr; const int *col = P.col; const double *val = P.val;
+                const int64_t nr = P.nrows, nc = P.ncols, nz = P.nnz; const bool r64 = P.rp64;
+                free_plan(P);
+                P = CsrPlan();
+                P.rowptr = rowptr; P.col = col; P.val = val; P.nrows = nr; P.ncols = nc; P.nnz = nz; P.rp64 = r64;
+                return build_plan_t<RP>(P, st, smaller, attempt + 1);
+              }
+              bst = 4; bct = 1;
+            }
             bst = env_int("PCGB_SPMV_STAGES", bst);
             bct = env_int("PCGB_SPMV_CTAS", bct);
             if (bst < 1) bst = 1;

@@ -26,9 +26,8 @@ if os.environ.get("SWEEP_MODEL", "hex") == "concrete":
 else:
     default = [
         {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
-        {**BSR, "PCGB_SPMV_TILE": 4362, "PCGB_BSR_INPLACE": 0},
-        *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_BSR_INPLACE": 1} for t in (4900, 5200, 5386, 5600, 5750, 5850)],
-        {**BSR, "PCGB_SPMV_TILE": 5386, "PCGB_BSR_INPLACE": 1, "PCGB_BSR_UNI": 0}]
+        {"PCGB_SPMV_BSR": 1},                                            # defaults: adaptive tile (largest with two CTAs per SM)
+        *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_BSR_INPLACE": 1} for t in (5850, 5920)]]
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
     for k, v in cfg.items():
