@@ -77,7 +77,7 @@ struct CsrPlan {
   // non-zero from HBM, a third of the x gathers and a ninth of the index loads of the row-group consumer
   bool bsr = false;
   uint16_t *bidx = nullptr;        // [nnz/9 + 16]  staged x position of block t of node n at rowptr[3n]/9 + t
-  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0, bsr_mode = 1;
+  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0, bsr_mode = 1, bsr_cw = 8;
   // interface-first split (multi-GPU overlap): tiles that own an interface row are listed first in desc_split
   struct TileDesc *desc_split = nullptr;  // [ntiles] permutation of tile_desc
   int nb_tiles = 0;                       // leading boundary tiles of desc_split
@@ -785,8 +785,8 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
 //     phase 2   (after one named barrier, scratch double-buffered by tile parity) thread r < R adds the partials of its
 //               row in block order -> y[r]: fixed summation order, bit-reproducible, no shuffles, no atomics.
 // Per 9 non-zeros: 13 shared-memory loads + 3 stores instead of 27 loads, and 8 + 2/9 bytes from HBM instead of 10.
-template <bool DOT, typename RP>
-__global__ void __launch_bounds__((kConsWarps + 4) * 32)
+template <bool DOT, int CW, typename RP>
+__global__ void __launch_bounds__((CW + 4) * 32)
 k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, const double *__restrict__ val,
             const double *__restrict__ x, double *__restrict__ y, const TileDesc *__restrict__ desc,
             const int *__restrict__ win_start, const int *__restrict__ win_off, int ntiles, int64_t nnz, int cap_nnz,
@@ -797,10 +797,10 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
   __shared__ uint64_t full_bar[8], empty_bar[8];
   __shared__ double red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nprod = (int)(blockDim.x >> 5) - kConsWarps;   // producer warps; stages % nprod == 0
+  const int nprod = (int)(blockDim.x >> 5) - CW;   // producer warps; stages % nprod == 0
 
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 34); mbar_init(&empty_bar[s], kConsWarps); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 34); mbar_init(&empty_bar[s], CW); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -819,9 +819,9 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
   double *spart = reinterpret_cast<double *>(smem_raw + (size_t)stages * stage_bytes);
   int *snbo = reinterpret_cast<int *>(spart + (size_t)2 * part_len);
 
-  if (warp >= kConsWarps) {
+  if (warp >= CW) {
     // ================= producer warp p (see k_spmv_persist): TMA val + block indices, cp.async node offsets + x windows
-    const int p = warp - kConsWarps;
+    const int p = warp - CW;
     const uint64_t pol = l2_evict_first_policy();
     int it = p;
     int tile = blockIdx.x + it * gridDim.x;
@@ -901,8 +901,8 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     return;
   }
 
-  // ================= consumer warps (kConsWarps * 32 threads, tid = consumer thread id)
-  constexpr int NT = kConsWarps * 32;
+  // ================= consumer warps (CW * 32 threads, tid = consumer thread id)
+  constexpr int NT = CW * 32;
   double dsum = 0.0;
   for (int it = 0;; ++it) {
     const int tile = blockIdx.x + it * gridDim.x;
@@ -991,7 +991,7 @@ k_spmv_bsr3(const RP *__restrict__ rowptr, const uint16_t *__restrict__ bidx, co
     if (lane == 0) red[warp] = v;
     named_bar_sync(1, NT);
     if (warp == 0) {
-      double t = lane < kConsWarps ? red[lane] : 0.0;
+      double t = lane < CW ? red[lane] : 0.0;
       t = warp_sum(t);
       if (lane == 0) dot_partials[blockIdx.x] = t;
     }
@@ -1356,6 +1356,8 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
             const bool inplace = env_int("PCGB_BSR_INPLACE", 1) != 0;
             P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (inplace ? 2 : 0);
+            P.bsr_cw = env_int("PCGB_BSR_CW", 8);
+            if (P.bsr_cw != 12 && P.bsr_cw != 16) P.bsr_cw = 8;
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
@@ -1502,20 +1504,30 @@ inline int launch_persist_lanes(const CsrPlan &P, const double *x, double *y, cu
   }
 }
 
-template <bool DOT, typename RP>
-inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
-                           int ntiles, int grid, double *dotp) {
-  auto kern = k_spmv_bsr3<DOT, RP>;
+template <bool DOT, int CW, typename RP>
+inline int launch_bsr_cw(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
+                         int ntiles, int grid, double *dotp) {
+  auto kern = k_spmv_bsr3<DOT, CW, RP>;
   if (skip == reinterpret_cast<const int *>(1)) {
     PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return PCGB_OK;
   }
   if (ntiles == 0) return PCGB_OK;
-  kern<<<grid, (kConsWarps + P.bsr_prod) * 32, P.smem_bsr, st>>>(static_cast<const RP *>(P.rowptr), P.bidx, P.val, x, y, desc, P.win_start,
+  kern<<<grid, (CW + P.bsr_prod) * 32, P.smem_bsr, st>>>(static_cast<const RP *>(P.rowptr), P.bidx, P.val, x, y, desc, P.win_start,
                                                                   P.win_off, ntiles, P.nnz, P.cap_nnz, P.cap_nodes, P.cap_x, P.cap_blocks,
                                                                   P.bsr_stages, P.bsr_stage_bytes, P.bsr_mode, dotp, skip);
   PCGB_CHECK_LAUNCH();
   return PCGB_OK;
+}
+
+template <bool DOT, typename RP>
+inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
+                           int ntiles, int grid, double *dotp) {
+  switch (P.bsr_cw) {   // consumer warps per CTA
+    case 12: return launch_bsr_cw<DOT, 12, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    case 16: return launch_bsr_cw<DOT, 16, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    default: return launch_bsr_cw<DOT, 8, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  }
 }
 
 inline int launch_persist_any(const CsrPlan &P, const double *x, double *y, bool with_dot, cudaStream_t st, const int *skip,

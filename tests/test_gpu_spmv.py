@@ -276,10 +276,10 @@ def test_release_col(cuda):
         assert not P.release_col() and P.col is not None
 
 
-@pytest.mark.parametrize("inplace", [1, 0])
+@pytest.mark.parametrize("inplace,cw", [(1, 8), (0, 8), (1, 16), (1, 12)])
 @pytest.mark.parametrize("uni", [1, 0])
 @pytest.mark.parametrize("tile", [0, 600, 1200, 2058])
-def test_spmv_node_block_kernel(cuda, monkeypatch, tile, uni, inplace):
+def test_spmv_node_block_kernel(cuda, monkeypatch, tile, uni, inplace, cw):
     """Node-block ("BSR-3") kernel, the default for 3-dofs-per-node matrices: one thread per 3x3 block, one 16-bit staged position
     per block (8 + 2/9 B per non-zero), rows summed from shared-memory partials in block order.  Several tile sizes (one and
     several passes of 256 blocks, 2- and 4-stage rings), clamped / interior boxes, fused dot, bit-reproducibility."""
@@ -287,7 +287,8 @@ def test_spmv_node_block_kernel(cuda, monkeypatch, tile, uni, inplace):
     from pcg_mpi_solver_b200.csr import CsrMatrix
     monkeypatch.setenv("PCGB_BSR_MIN_UNIFORM_PCT", "0")     # small boxes are mostly boundary: do not let the regularity gate decide
     monkeypatch.setenv("PCGB_BSR_UNI", str(uni))            # uniform-tile fast path on / off (off: per-block node search everywhere)
-    monkeypatch.setenv("PCGB_BSR_INPLACE", str(inplace))    # row partials in the stage itself (3-stage ring) / in a separate scratch
+    monkeypatch.setenv("PCGB_BSR_INPLACE", str(inplace))    # row partials in the stage itself (larger stages) / in a separate scratch
+    monkeypatch.setenv("PCGB_BSR_CW", str(cw))              # consumer warps per CTA
     if tile:
         monkeypatch.setenv("PCGB_SPMV_TILE", str(tile))
     for box in [((9, 7, 5), (0, 0, 0), (9, 7, 5)), ((8, 6, 4), (4, 0, 2), (4, 3, 2)), ((14, 12, 10), (0, 0, 0), (14, 12, 10))]:

@@ -26,10 +26,12 @@ if os.environ.get("SWEEP_MODEL", "hex") == "concrete":
 else:
     default = [
         {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
-        {"PCGB_SPMV_BSR": 1},                                            # defaults: adaptive tile (largest with two CTAs per SM)
-        *[{**BSR, "PCGB_SPMV_TILE": t, "PCGB_BSR_INPLACE": 1} for t in (5850, 5920)]]
+        {"PCGB_SPMV_BSR": 1},                                            # library defaults: adaptive tile (largest with two CTAs per SM)
+        {"PCGB_BSR_CW": 12}, {"PCGB_BSR_CW": 16}, {"PCGB_BSR_CW": 16, "PCGB_BSR_UNI": 0}]
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
+    for k in [k for k in os.environ if k.startswith("PCGB_")]:   # every config starts from the library defaults
+        del os.environ[k]
     for k, v in cfg.items():
         os.environ[k] = str(v)
     M = CsrMatrix(base.rowptr, base.col, base.val, base.shape)
