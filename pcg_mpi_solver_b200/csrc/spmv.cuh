@@ -1357,7 +1357,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
             const bool inplace = env_int("PCGB_BSR_INPLACE", 1) != 0;
             P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (inplace ? 2 : 0);
             P.bsr_cw = env_int("PCGB_BSR_CW", 8);
-            if (P.bsr_cw != 12 && P.bsr_cw != 16) P.bsr_cw = 8;
+            if (P.bsr_cw != 4 && P.bsr_cw != 6 && P.bsr_cw != 12 && P.bsr_cw != 16) P.bsr_cw = 8;
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
@@ -1524,6 +1524,8 @@ template <bool DOT, typename RP>
 inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
                            int ntiles, int grid, double *dotp) {
   switch (P.bsr_cw) {   // consumer warps per CTA
+    case 4: return launch_bsr_cw<DOT, 4, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+    case 6: return launch_bsr_cw<DOT, 6, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
     case 12: return launch_bsr_cw<DOT, 12, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
     case 16: return launch_bsr_cw<DOT, 16, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
     default: return launch_bsr_cw<DOT, 8, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);

@@ -27,7 +27,7 @@ else:
     default = [
         {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
         {"PCGB_SPMV_BSR": 1},                                            # library defaults: adaptive tile (largest with two CTAs per SM)
-        {"PCGB_BSR_CW": 12}, {"PCGB_BSR_CW": 16}, {"PCGB_BSR_CW": 16, "PCGB_BSR_UNI": 0}]
+        {"PCGB_BSR_CW": 6}, {"PCGB_BSR_CW": 4}, {"PCGB_BSR_CW": 6, "PCGB_SPMV_CTAS": 3, "PCGB_SPMV_TILE": 3800}, {"PCGB_BSR_CW": 4, "PCGB_SPMV_CTAS": 3, "PCGB_SPMV_TILE": 3800}]
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
     for k in [k for k in os.environ if k.startswith("PCGB_")]:   # every config starts from the library defaults
