@@ -77,7 +77,7 @@ struct CsrPlan {
   // non-zero from HBM, a third of the x gathers and a ninth of the index loads of the row-group consumer
   bool bsr = false;
   uint16_t *bidx = nullptr;        // [nnz/9 + 16]  staged x position of block t of node n at rowptr[3n]/9 + t
-  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0, bsr_mode = 1, bsr_cw = 8;
+  int cap_blocks = 0, cap_nodes = 0, smem_bsr = 0, bsr_stage_bytes = 0, bsr_stages = 0, bsr_prod = 0, grid_bsr = 0, bsr_mode = 1, bsr_cw = 6;
   // interface-first split (multi-GPU overlap): tiles that own an interface row are listed first in desc_split
   struct TileDesc *desc_split = nullptr;  // [ntiles] permutation of tile_desc
   int nb_tiles = 0;                       // leading boundary tiles of desc_split
@@ -1356,8 +1356,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
             const bool inplace = env_int("PCGB_BSR_INPLACE", 1) != 0;
             P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (inplace ? 2 : 0);
-            P.bsr_cw = env_int("PCGB_BSR_CW", 8);
-            if (P.bsr_cw != 4 && P.bsr_cw != 6 && P.bsr_cw != 12 && P.bsr_cw != 16) P.bsr_cw = 8;
+            P.bsr_cw = env_int("PCGB_BSR_CW", 6) == 8 ? 8 : 6;
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
@@ -1523,13 +1522,10 @@ inline int launch_bsr_cw(const CsrPlan &P, const double *x, double *y, cudaStrea
 template <bool DOT, typename RP>
 inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStream_t st, const int *skip, const TileDesc *desc,
                            int ntiles, int grid, double *dotp) {
-  switch (P.bsr_cw) {   // consumer warps per CTA
-    case 4: return launch_bsr_cw<DOT, 4, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
-    case 6: return launch_bsr_cw<DOT, 6, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
-    case 12: return launch_bsr_cw<DOT, 12, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
-    case 16: return launch_bsr_cw<DOT, 16, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
-    default: return launch_bsr_cw<DOT, 8, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
-  }
+  // consumer warps per CTA: 6 won the B200 sweeps by a hair (0.762 ms; 8: 0.772, 4: 0.783, 12: 0.794, 16: 0.919;
+  // profiles/spmv_sweep_r2n_consumer_warps.txt, spmv_sweep_r2o.txt)
+  if (P.bsr_cw == 8) return launch_bsr_cw<DOT, 8, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  return launch_bsr_cw<DOT, 6, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
 }
 
 inline int launch_persist_any(const CsrPlan &P, const double *x, double *y, bool with_dot, cudaStream_t st, const int *skip,

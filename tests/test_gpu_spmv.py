@@ -276,7 +276,7 @@ def test_release_col(cuda):
         assert not P.release_col() and P.col is not None
 
 
-@pytest.mark.parametrize("inplace,cw", [(1, 8), (0, 8), (1, 16), (1, 12)])
+@pytest.mark.parametrize("inplace,cw", [(1, 6), (0, 6), (1, 8), (0, 8)])
 @pytest.mark.parametrize("uni", [1, 0])
 @pytest.mark.parametrize("tile", [0, 600, 1200, 2058])
 def test_spmv_node_block_kernel(cuda, monkeypatch, tile, uni, inplace, cw):
