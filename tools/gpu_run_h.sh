@@ -4,19 +4,22 @@ mkdir -p gpurun_out
 T=${1:-r2h}
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -rs > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"
 tail -15 gpurun_out/${T}_pytest.log
+if [ "$2" = "concrete" ]; then
 SWEEP_MODEL=concrete timeout 400 python tools/spmv_sweep.py > gpurun_out/${T}_sweep_concrete.txt 2> gpurun_out/${T}_sweep_concrete.err; echo "sweep concrete rc=$?"
 cat gpurun_out/${T}_sweep_concrete.txt; tail -3 gpurun_out/${T}_sweep_concrete.err
-timeout 300 python tools/spmv_sweep.py > gpurun_out/${T}_sweep.txt 2> gpurun_out/${T}_sweep.err; cat gpurun_out/${T}_sweep.txt
+fi
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --operator ebe > gpurun_out/${T}_bench_n1_ebe.json 2> gpurun_out/${T}_bench_n1_ebe.err; echo "bench ebe rc=$?"
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu --workload concrete > gpurun_out/${T}_bench_n1_concrete.json 2> gpurun_out/${T}_bench_n1_concrete.err; echo "bench concrete rc=$?"
 timeout 400 python bench.py --steps 200 --warmup 20 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; echo "bench rc=$?"
 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${T}_bench_n1_k20.json 2> gpurun_out/${T}_bench_n1_k20.err; echo "bench k20 rc=$?"
 timeout 600 python bench.py --steps 200 --warmup 20 --no-cpu --block 256 > gpurun_out/${T}_bench_n1_b256.json 2> gpurun_out/${T}_bench_n1_b256.err; echo "bench b256 rc=$?"
 python - <<PY
 import json
-for f in ("bench_n1", "bench_n1_k20", "bench_n1_b256"):
+for f in ("bench_n1", "bench_n1_k20", "bench_n1_b256", "bench_n1_ebe", "bench_n1_concrete"):
     try:
         d=json.loads(open("gpurun_out/${T}_%s.json" % f).read().strip().splitlines()[-1])
         print(f, "ms/iter", round(d["ms_per_step"],4), "it/s", round(d["iterations_per_s"],1), "e2e frac", round(d["e2e"]["fraction_of_value"],3), "spmv", round(d["roofline"]["mean_launch_ms"],4), "frac", round(d["roofline"]["frac"],3),
-              "streamed frac", round(d["roofline"]["streamed_frac_of_peak"],3), "parity", d["parity"]["max_rel_err"], d["parity"]["ok"], "cpu", (d.get("cpu_baseline") or {}).get("value"))
+              "streamed frac", round(d["roofline"]["streamed_frac_of_peak"],3), "parity", d["parity"]["max_rel_err"], d["parity"]["ok"], "cpu", (d.get("cpu_baseline") or {}).get("value"), "clocks", d["clocks"], "full", d.get("full_solve"))
     except Exception as e:
         print(f, "failed", e)
 PY
