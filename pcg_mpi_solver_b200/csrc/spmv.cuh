@@ -67,7 +67,7 @@ struct CsrPlan {
   // persistent pipelined variant (k_spmv_persist)
   bool persist = false;
   struct TileDesc *tile_desc = nullptr;  // [ntiles]
-  int stages = 0, stage_bytes = 0, smem_persist = 0, grid_persist = 0, ctas_per_sm = 1;
+  int stages = 0, stage_bytes = 0, smem_persist = 0, grid_persist = 0, ctas_per_sm = 1, persist_prod = 4;
   // column-triple index ("T3"): when every row is a sequence of aligned triples of consecutive staged positions
   // (3 dofs per node: hex / concrete), ONE 16-bit index is stored per triple -> 8 + 2/3 bytes per non-zero
   bool t3 = false;
@@ -518,7 +518,7 @@ k_spmv_staged(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx, 
 //   consumer warps:           wait full[s] -> sub-warp groups reduce the rows out of shared memory,
 //                             group leaders write y (and accumulate x.y) -> arrive empty[s]
 // Consumers never wait on a global load; HBM streaming is entirely asynchronous (UBLKCP) and `stages` tiles deep.
-constexpr int kProd = 4;          // producer warps = stages served round-robin
+constexpr int kProd = 4;          // at most this many producer warps (= min(4, stages)); stages % producers == 0
 constexpr int kConsWarps = 8;
 constexpr int kPersistThreads = (kConsWarps + kProd) * 32;
 
@@ -582,7 +582,8 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
   const size_t off_sidx = off_srp + (size_t)(cap_rows + 2) * 8, off_meta = (off_sidx + (size_t)cap_idx * 2 + 15) & ~(size_t)15;
 
   if (warp >= kConsWarps) {
-    // ================= producer warp p: tiles it = p, p + kProd, ... (stage = it % stages, stages % kProd == 0)
+    // ================= producer warp p: tiles it = p, p + nprod, ... (stage = it % stages, stages % nprod == 0)
+    const int nprod = (int)(blockDim.x >> 5) - kConsWarps;
     // Software-pipelined: the descriptor and the window descriptors of the NEXT tile are fetched while the
     // current one is being issued, so the only thing a stage waits for is its own TMA flight.
     const int p = warp - kConsWarps;
@@ -600,7 +601,7 @@ k_spmv_persist(const RP *__restrict__ rowptr, const uint16_t *__restrict__ lidx,
     while (have) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)((it / stages) & 1);
-      const int nit = it + kProd;
+      const int nit = it + nprod;
       const int ntile = blockIdx.x + nit * gridDim.x;
       const bool nhave = ntile < ntiles;
       int4 nd0 = make_int4(0, 0, 0, 0), nd1 = make_int4(0, 0, 0, 0);
@@ -1327,9 +1328,10 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
           P.stage_bytes = P.cap_nnz * 8 + P.cap_x * 8 + (P.cap_rows + 2) * 8 + ((cap_idx * 2 + 15) & ~15) + 32;
           P.stage_bytes = (P.stage_bytes + 127) & ~127;
           int stages = env_int("PCGB_SPMV_STAGES", 4);
-          if (stages < kProd) stages = kProd;
+          if (stages < 1) stages = 1;
           if (stages > 8) stages = 8;
-          stages -= stages % kProd;
+          P.persist_prod = stages >= kProd ? kProd : stages;
+          stages -= stages % P.persist_prod;
           const int ctas = env_int("PCGB_SPMV_CTAS", 2);
           P.stages = stages;
           P.smem_persist = stages * P.stage_bytes;
@@ -1485,7 +1487,7 @@ inline int launch_persist_inst(const CsrPlan &P, const double *x, double *y, cud
     return PCGB_OK;
   }
   if (ntiles == 0) return PCGB_OK;
-  kern<<<grid, kPersistThreads, P.smem_persist, st>>>(static_cast<const RP *>(P.rowptr), T3 ? P.lidx3 : P.lidx, P.val, x, y, desc,
+  kern<<<grid, (kConsWarps + P.persist_prod) * 32, P.smem_persist, st>>>(static_cast<const RP *>(P.rowptr), T3 ? P.lidx3 : P.lidx, P.val, x, y, desc,
                                                        P.win_start, P.win_off, ntiles, P.nnz, P.cap_nnz, P.cap_rows, P.cap_x,
                                                        P.stages, P.stage_bytes, P.carry, dotp, skip);
   PCGB_CHECK_LAUNCH();

@@ -19,15 +19,15 @@ x = torch.randn(base.shape[1], dtype=torch.float64, device=dev)
 y = torch.empty_like(x)
 BSR = {"PCGB_SPMV_BSR": 1, "PCGB_SPMV_CTAS": 2, "PCGB_SPMV_STAGES": 2}
 if os.environ.get("SWEEP_MODEL", "hex") == "concrete":
-    default = [{"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2} for l in (8, 16, 32) for t in (1536, 1792, 2048, 2304)] + [
-        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1280, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3},
-        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1792, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2, "PCGB_SPMV_GAP": 32},
-        {"PCGB_BSR_MIN_UNIFORM_PCT": 0, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2}]
+    default = [{"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1792, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2}] + [
+        {"PCGB_SPMV_LANES": l, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2} for l in (8, 16) for t in (2400, 2800, 3200, 3600)] + [
+        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 2000, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 3},
+        {"PCGB_SPMV_LANES": 16, "PCGB_SPMV_TILE": 1280, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 3}]
 else:
     default = [
         {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
         {"PCGB_SPMV_BSR": 1},                                            # library defaults: adaptive tile (largest with two CTAs per SM)
-        {"PCGB_BSR_CW": 6}, {"PCGB_BSR_CW": 4}, {"PCGB_BSR_CW": 6, "PCGB_SPMV_CTAS": 3, "PCGB_SPMV_TILE": 3800}, {"PCGB_BSR_CW": 4, "PCGB_SPMV_CTAS": 3, "PCGB_SPMV_TILE": 3800}]
+        *[{"PCGB_SPMV_BSR": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2} for t in (3600, 4200, 4600)]]
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
     for k in [k for k in os.environ if k.startswith("PCGB_")]:   # every config starts from the library defaults
