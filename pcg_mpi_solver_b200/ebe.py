@@ -1,10 +1,10 @@
-"""EXPERIMENTAL matrix-free element-by-element operator - the reference's own operator form
+"""Opt-in matrix-free element-by-element operator - the reference's own operator form
 (calcMatVecProd, pcg_solver.py:263-300) on the GPU instead of the assembled CSR matrix.
 
-Status: written at the end of round 1; its parity tests (tests/test_gpu_ebe.py: hex vs CSR/oracle, concrete vs the
-reference's 1085 iterations) are green on a B200 and a first timing exists (profiles/ebe_quick_r1.json: 0.27 ms per
-application and 2550 PCG it/s on the 128^3 hex box, vs 0.93 ms / 964 it/s for the CSR kernel), but it has not been
-profiled or tuned and scatter-adds with fp64 atomics (not bit-reproducible).  Opt-in: `to_operator(kind="ebe")`.
+Status: parity-green on B200 (tests/test_gpu_ebe.py: hex vs CSR/oracle, concrete vs the reference's 1085 iterations, several
+live operators with different pattern matrices); [B200] 128^3: 0.27 ms per application, 2589 PCG it/s (`bench.py --operator ebe`,
+profiles/bench_r2p_n1_ebe.json) against 0.80 ms / 1116 it/s for the CSR node-block kernel.  Scatter-adds with fp64 atomics
+(reproducible to rounding only); `EbeMatrixColored` is the bit-reproducible coloured variant (3x slower).  `to_operator(kind="ebe")`.
 """
 from __future__ import annotations
 
@@ -84,7 +84,7 @@ class EbeMatrix:
 
 
 class EbeMatrixColored:
-    """ROUND-2 PREPARATION (not yet run on hardware; operator-level only): the same operator with an atomics-free,
+    """Operator-level variant (green on B200, tests/test_gpu_ebe_colored.py): the same operator with an atomics-free,
     bit-reproducible scatter.  All elements of the subdomain are coloured together (coloring.color_elements: no two
     elements of a colour share a node), every (pattern group, colour) slice becomes its own group, slices are passed
     in colour order and the kernels of one colour use plain `y[dof] += v` (csrc/ebe_color.cuh)."""

@@ -52,6 +52,7 @@ class Communicator:
         self._h = ctypes.c_void_p()
         self._allgather = allgather
         self.peer_error = None
+        self._has_nccl = unique_id is not None
         uid = (ctypes.c_ubyte * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().pcgb_comm_create(rank, nranks, uid, ctypes.byref(self._h)), "pcgb_comm_create")
@@ -64,6 +65,7 @@ class Communicator:
         lib = _lib.load()
         self._allgather = allgather
         self.peer_error = None
+        self._has_nccl = unique_id is not None
         blob = (ctypes.c_ubyte * _lib.IPC_BLOB_BYTES)()
         ok = True
         with torch.cuda.device(self.device):
@@ -187,12 +189,25 @@ class SubdomainOperator:
                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.n,
                                                 ctypes.byref(self._halo)), "pcgb_halo_create")
                 if comm.transport == "peer" and comm._allgather is not None:
+                    # collective: every rank exports, all-gathers and imports; if ANY rank fails (no CUDA IPC here) the whole
+                    # communicator goes back to the NCCL transport so that all ranks stay on the same path
                     nb = int(lib.pcgb_halo_blob_bytes(self._halo))
                     blob = (ctypes.c_ubyte * nb)()
-                    _lib.check(lib.pcgb_halo_export(self._halo, blob), "pcgb_halo_export")
-                    blobs = comm._allgather(bytes(blob))
-                    buf = (ctypes.c_ubyte * (nb * comm.nranks)).from_buffer_copy(b"".join(blobs))
-                    _lib.check(lib.pcgb_halo_import(self._halo, buf), "pcgb_halo_import")
+                    ok = lib.pcgb_halo_export(self._halo, blob) == 0
+                    err = None if ok else lib.pcgb_last_error().decode()
+                    blobs = comm._allgather(bytes(blob) if ok else b"")
+                    if all(len(b) == nb for b in blobs):
+                        buf = (ctypes.c_ubyte * (nb * comm.nranks)).from_buffer_copy(b"".join(blobs))
+                        ok = lib.pcgb_halo_import(self._halo, buf) == 0
+                        err = None if ok else lib.pcgb_last_error().decode()
+                    else:
+                        ok = False
+                    if not all(o == b"1" for o in comm._allgather(b"1" if ok else b"0")):
+                        comm.peer_error = err or "a peer rank could not map the halo block"
+                        if comm._has_nccl:
+                            comm.set_transport("nccl")
+                        else:
+                            raise _lib.PcgbError(f"halo exchange over peer memory is not available ({comm.peer_error}) and the communicator has no NCCL")
             create = lib.pcgb_solver_create if isinstance(A, CsrMatrix) else lib.pcgb_solver_create_ebe  # EbeMatrix: experimental
             _lib.check(create(A.handle, self._halo if self._halo else None,
                               comm.handle if comm is not None else None, ctypes.byref(self._solver)), "pcgb_solver_create")

@@ -79,3 +79,29 @@ def test_bench_reference_arm_schema():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_bench_parity_checker_and_goldens():
+    """bench.py's parity block: the committed oracle goldens exist for every GPU count of the default workload, an exact history
+    passes, a perturbed one fails (the bench then exits with code 3), a missing golden is reported as such."""
+    import importlib.util
+    import json
+
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n in (1, 2, 4, 8):
+        gold, path = bench.golden_resvec(128, n)
+        assert gold is not None and len(gold["resvec"]) == 41 and gold["n_gpus"] == n, path
+        res = bench.resvec_parity(np.array(gold["resvec"][:21]), gold["normb"], gold, path)
+        assert res["ok"] is True and res["max_rel_err"] == 0.0 and res["checked_iterations"] == 10
+        bad = np.array(gold["resvec"][:21])
+        bad[7] *= 1 + 1e-7
+        assert bench.resvec_parity(bad, gold["normb"], gold, path)["ok"] is False
+        assert bench.resvec_parity(np.array(gold["resvec"][:21]), gold["normb"] * (1 + 1e-6), gold, path)["ok"] is False
+    gold, path = bench.golden_resvec(96, 3)
+    assert gold is None and bench.resvec_parity(np.ones(5), 1.0, gold, path)["ok"] is None
+    # the 1e8-dof goldens of the north-star size (160^3 per GPU at 8 GPUs = 320^3 elements)
+    g160, _ = bench.golden_resvec(160, 8)
+    assert g160 is not None and g160["n_global"] == 3 * 320 * 321 * 321
