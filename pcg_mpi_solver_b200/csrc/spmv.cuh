@@ -1358,7 +1358,8 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
             P.bsr_stage_bytes = (P.bsr_stage_bytes + 127) & ~127;
             const bool inplace = env_int("PCGB_BSR_INPLACE", 1) != 0;
             P.bsr_mode = (env_int("PCGB_BSR_UNI", 1) ? 1 : 0) | (inplace ? 2 : 0);
-            P.bsr_cw = env_int("PCGB_BSR_CW", 6) == 8 ? 8 : 6;
+            P.bsr_cw = env_int("PCGB_BSR_CW", 6);
+            if (P.bsr_cw != 8 && P.bsr_cw != 12) P.bsr_cw = 6;
             const int scratch = (inplace ? 0 : 6 * P.cap_blocks * 8) + 2 * (P.cap_nodes + 2) * 4 + 64;
             // 2 CTAs x 4 stages when they fit, else 2 CTAs x 2 stages (2 producer warps), else 1 CTA x 4 stages
             int bst = 2, bct = 2;
@@ -1527,6 +1528,7 @@ inline int launch_bsr_inst(const CsrPlan &P, const double *x, double *y, cudaStr
   // consumer warps per CTA: 6 won the B200 sweeps by a hair (0.762 ms; 8: 0.772, 4: 0.783, 12: 0.794, 16: 0.919;
   // profiles/spmv_sweep_r2n_consumer_warps.txt, spmv_sweep_r2o.txt)
   if (P.bsr_cw == 8) return launch_bsr_cw<DOT, 8, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
+  if (P.bsr_cw == 12) return launch_bsr_cw<DOT, 12, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
   return launch_bsr_cw<DOT, 6, RP>(P, x, y, st, skip, desc, ntiles, grid, dotp);
 }
 

@@ -27,7 +27,9 @@ else:
     default = [
         {"PCGB_SPMV_BSR": 0, "PCGB_SPMV_T3": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": 2304, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_CTAS": 2},      # round-1 kernel
         {"PCGB_SPMV_BSR": 1},                                            # library defaults: adaptive tile (largest with two CTAs per SM)
-        *[{"PCGB_SPMV_BSR": 0, "PCGB_SPMV_LANES": 8, "PCGB_SPMV_TILE": t, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_CTAS": 2} for t in (3600, 4200, 4600)]]
+        *[{"PCGB_SPMV_CTAS": 1, "PCGB_SPMV_STAGES": 2, "PCGB_SPMV_TILE": t, "PCGB_BSR_CW": cw} for t in (9000, 11500) for cw in (8, 12)],
+        {"PCGB_SPMV_CTAS": 1, "PCGB_SPMV_STAGES": 3, "PCGB_SPMV_TILE": 7600, "PCGB_BSR_CW": 12},
+        {"PCGB_SPMV_CTAS": 1, "PCGB_SPMV_STAGES": 4, "PCGB_SPMV_TILE": 5800, "PCGB_BSR_CW": 12}]
 configs = json.loads(os.environ.get("SWEEP_CONFIGS", "[]")) or default
 for cfg in configs:
     for k in [k for k in os.environ if k.startswith("PCGB_")]:   # every config starts from the library defaults
