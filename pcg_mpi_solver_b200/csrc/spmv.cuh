@@ -1386,7 +1386,7 @@ inline int build_plan_t(CsrPlan &P, cudaStream_t st, int bsr_tile = 0, int attem
             P.smem_bsr = bst * P.bsr_stage_bytes + scratch;
             int bfit = (227 * 1024) / (P.smem_bsr + 2048);
             if (bfit < 1) bfit = 1;
-            P.bsr = h_fb == 0 && P.smem_bsr <= 200 * 1024;
+            P.bsr = h_fb == 0 && P.smem_bsr <= 226 * 1024;
             if (P.bsr) {
               // uniform tiles (every node of the tile has the same number of blocks) take the search-free path
               PCGB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
@@ -1511,7 +1511,7 @@ inline int launch_bsr_cw(const CsrPlan &P, const double *x, double *y, cudaStrea
                          int ntiles, int grid, double *dotp) {
   auto kern = k_spmv_bsr3<DOT, CW, RP>;
   if (skip == reinterpret_cast<const int *>(1)) {
-    PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PCGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     return PCGB_OK;
   }
   if (ntiles == 0) return PCGB_OK;
