@@ -191,7 +191,7 @@ k_halo_pack_peer(PeerHalo h, const int *__restrict__ idx, const double *__restri
   }
   __syncthreads();
   if (!s_last) return;
-  // (the release store orders everything this thread has observed - the other CTAs' fenced stores through the counter - first)
+  __threadfence_system();   // belt and braces: the flag-writing threads learnt of the other CTAs' completion through thread 0
   if ((int)threadIdx.x < h.n_nbr) st_release_sys(h.remote_flag[threadIdx.x] + par, ep);
   if (threadIdx.x == 0) { *h.done = 0; *h.epoch = ep; }
 }
