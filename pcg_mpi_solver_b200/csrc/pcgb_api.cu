@@ -37,14 +37,15 @@ struct pcgb_ebe2_s {
 struct GraphKey {
   const void *minv, *w, *xb0, *resvec;
   int iters;
+  int variant;   // what the captured iteration looks like: bit 0 peer transport, bit 1 interface-first split, bit 2 forked unpack
   bool operator==(const GraphKey &o) const {
-    return minv == o.minv && w == o.w && xb0 == o.xb0 && resvec == o.resvec && iters == o.iters;
+    return minv == o.minv && w == o.w && xb0 == o.xb0 && resvec == o.resvec && iters == o.iters && variant == o.variant;
   }
 };
 
 struct pcgb_solver_s {
   pcgb_csr_t A = nullptr;
-  pcgb_ebe_t E = nullptr;       // experimental matrix-free operator (exactly one of A / E is set)
+  pcgb_ebe_t E = nullptr;       // opt-in matrix-free operator (exactly one of A / E is set)
   pcgb_halo_t halo = nullptr;
   pcgb_comm_t comm = nullptr;
   int64_t n = 0;
@@ -62,7 +63,7 @@ struct pcgb_solver_s {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_l0 = nullptr, ev_l1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
   std::vector<cudaEvent_t> ev_k;  // SpMV brackets (time_kernels)
   cudaGraphExec_t gexec = nullptr;
-  GraphKey gkey{nullptr, nullptr, nullptr, nullptr, 0};
+  GraphKey gkey{nullptr, nullptr, nullptr, nullptr, 0, 0};
   int launches = 0;             // launches issued outside graphs (running counter per solve)
   int launches_per_iter = 0;
   bool fork_halo = true;        // PCGB_FORK=0 keeps the unpack on the main stream
@@ -551,7 +552,7 @@ int pcgb_halo_exchange_add(pcgb_halo_t h, double *d_y, void *stream) {
 
 int64_t pcgb_halo_bytes(pcgb_halo_t h) { return h ? h->m * 8 : 0; }
 
-// ------------------------------------------------------------------------------------ EBE operator (experimental)
+// ------------------------------------------------------------------------------------ EBE operator (opt-in, f1)
 int pcgb_ebe_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, pcgb_ebe_t *out) {
   if (!out || n < 0 || ngroups < 0 || (ngroups > 0 && !groups)) return fail(PCGB_ERR_ARG, "pcgb_ebe_create: bad argument");
   if (n >= (1 << 30)) return fail(PCGB_ERR_ARG, "pcgb_ebe_create: more than 2^30 dofs");
@@ -659,7 +660,7 @@ int pcgb_assemble_destroy(pcgb_asm_t a) {
   return PCGB_OK;
 }
 
-// ------------------------------------------------------------------------------------ coloured EBE operator (round-2 prep)
+// ------------------------------------------------------------------------------------ coloured EBE operator (operator level)
 // groups[] holds one entry per (pattern group, colour), sorted by colour; phase[g] is the colour.  Pattern matrices of
 // the 24-dof groups are de-duplicated into the constant-memory slots by content of ke_host (same pointer = same slot).
 int pcgb_ebe2_create(int64_t n, int ngroups, const pcgb_ebe_group *groups, const int32_t *phase, pcgb_ebe2_t *out) {
@@ -1128,7 +1129,8 @@ static int solve_on(pcgb_solver_t s, const double *d_b, const double *d_minv, co
   for (;;) {
     // ---- enqueue `batch` iterations
     if (want_graph && batch > 1) {
-      GraphKey key{d_minv, d_w, xw, d_resvec, batch};
+      const int variant = (peer_path(s) ? 1 : 0) | ((s->A && spmv_split_available(s->A->P)) ? 2 : 0) | (s->fork_halo ? 4 : 0);
+      GraphKey key{d_minv, d_w, xw, d_resvec, batch, variant};
       if (!s->gexec || !(s->gkey == key)) {
         if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
         cudaGraph_t graph = nullptr;

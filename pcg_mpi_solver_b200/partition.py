@@ -104,7 +104,7 @@ class SubdomainData:
 
     def to_operator(self, comm=None, device="cuda", kind: str = "csr"):
         """Upload A and build the halo plan: the `A` argument of solve() for this rank.
-        kind="ebe" selects the EXPERIMENTAL matrix-free operator (ebe.py) instead of the assembled CSR matrix."""
+        kind="ebe" selects the opt-in matrix-free operator (ebe.py) instead of the assembled CSR matrix."""
         from .csr import CsrMatrix
         from .solver import SubdomainOperator
         if kind == "ebe":

@@ -208,7 +208,7 @@ class SubdomainOperator:
                             comm.set_transport("nccl")
                         else:
                             raise _lib.PcgbError(f"halo exchange over peer memory is not available ({comm.peer_error}) and the communicator has no NCCL")
-            create = lib.pcgb_solver_create if isinstance(A, CsrMatrix) else lib.pcgb_solver_create_ebe  # EbeMatrix: experimental
+            create = lib.pcgb_solver_create if isinstance(A, CsrMatrix) else lib.pcgb_solver_create_ebe  # EbeMatrix: opt-in matrix-free operator
             _lib.check(create(A.handle, self._halo if self._halo else None,
                               comm.handle if comm is not None else None, ctypes.byref(self._solver)), "pcgb_solver_create")
 
