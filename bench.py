@@ -365,6 +365,7 @@ def main():
         log(f"preflight parity: {preflight}")
 
     if args.workload == "hex":
+        setup_extra = None
         blocks = partition_blocks(ng, pgrid)
         blk = blocks[rank]
         blk.h = 1.0 / ng[0]
@@ -399,7 +400,11 @@ def main():
             config["workload"] = config["workload"].replace("trilinear hex elastostatics", f"trilinear hex elastostatics, METIS {world}-way element partition")
         sub = subs[rank]
         n_global = sub.n_global_eff
-        op = sub.to_operator(comm, device=dev, kind=args.operator)
+        torch.cuda.synchronize()
+        t_asm = time.perf_counter()
+        op = sub.to_operator(comm, device=dev, kind=args.operator)      # device assembly of K_i[Eff,Eff] (csrc/assemble.cuh) + SpMV plan + halo plan
+        torch.cuda.synchronize()
+        setup_extra = {"assemble_and_plan_s": time.perf_counter() - t_asm, "elements": int(sum(g.ck.size for g in sub.groups)), "pattern_groups": len(sub.groups)}
         A = op.A
         b = torch.from_numpy(sub.b).to(dev)
         del subs
@@ -511,6 +516,7 @@ def main():
                 "details": dict(operator=args.operator, n_per_gpu=n, nnz_per_gpu=A.nnz if is_csr else A.nnz_equivalent, n_global=n_global,
                                 plan=A.plan_info() if is_csr else {"kernel": "k_ebe_t24", "pattern_groups": 1}, col_released=col_released,
                                 halo_bytes_per_exchange=op.halo_bytes(), transport=comm.transport if comm else None, metis_parts=world if args.workload != "hex" else None,
+                                builder=setup_extra,
                                 nvlink_bytes_per_iteration_per_gpu=(2 * op.halo_bytes() + (2 * 48 * (world - 1) if comm and comm.transport == "peer" else 0)) if comm else 0),
                 "iterations_per_s": its, "dof_iterations_per_s": its * n_global,
                 "e2e": {"value": (world if weak else 1) * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n / K, "d2h_bytes_per_step": 8 * n / K,
