@@ -26,3 +26,4 @@ run n8_b160 8 PCGB_COMM=peer -- --steps 200 --warmup 20 --no-cpu --block 160
 run n8_concrete 8 PCGB_COMM=peer -- --steps 200 --warmup 20 --no-cpu --workload concrete
 run n8_hexmetis 8 PCGB_COMM=peer -- --steps 200 --warmup 20 --no-cpu --workload hex_metis --block 64
 run n4_peer 4 PCGB_COMM=peer -- --steps 200 --warmup 20 --no-cpu
+run n8_b256 8 PCGB_COMM=peer -- --steps 100 --warmup 10 --no-cpu --block 256
