@@ -65,7 +65,6 @@ class Communicator:
         lib = _lib.load()
         self._allgather = allgather
         self.peer_error = None
-        self._has_nccl = unique_id is not None
         blob = (ctypes.c_ubyte * _lib.IPC_BLOB_BYTES)()
         ok = True
         with torch.cuda.device(self.device):
