@@ -107,24 +107,13 @@ def test_bench_parity_checker_and_goldens():
     assert g160 is not None and g160["n_global"] == 3 * 320 * 321 * 321
 
 
-def _build_c_demo(out):
-    """gcc (plain C, no nvcc, no Python) against include/pcgb200.h + libpcgb200.so + the CUDA runtime."""
-    import subprocess
-    so_dir = os.path.join(ROOT, "pcg_mpi_solver_b200", "csrc")
-    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", os.path.join(ROOT, "examples", "cabi_demo.c"),
-           "-o", out, "-L" + so_dir, "-lpcgb200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + so_dir]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0, r.stdout
-    return out
-
-
-def test_c_demo_compiles_links_and_refuses_to_run_without_a_gpu(tmp_path):
+def test_c_demo_compiles_links_and_refuses_to_run_without_a_gpu(tmp_path, build_c_demo):
     """The boundary is a C ABI: a plain-C caller compiles and links against the header and the shared object; without a device it
     fails loudly (exit code 4) instead of falling back to anything."""
     import subprocess
 
     import torch
-    exe = _build_c_demo(str(tmp_path / "cabi_demo"))
+    exe = build_c_demo(str(tmp_path / "cabi_demo"))
     if torch.cuda.is_available():
         pytest.skip("GPU present: tests/test_gpu_cabi_demo.py runs it")
     r = subprocess.run([exe, "8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
